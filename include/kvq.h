@@ -1,0 +1,150 @@
+/* kvq.h -- C ABI of libkvq.so: the B200 (sm_100a) vector-quantisation bottleneck.
+ *
+ * This is the drop-in boundary for the hot path of dansolombrino/Kindergarten-VQ-VAE's hard VQ layer,
+ * reference file models/shelgon3/VectorQuantizer.py (class VectorQuantizer, forward at :31-93 and the
+ * autograd backward PyTorch derives from it).  The reference has no FFI of its own (it is pure PyTorch);
+ * each entry point below names the reference lines it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer, including the workspace (size from kvq_workspace_bytes);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the device
+ *     (except the *_host entry point, which is synchronous by contract);
+ *   - return value: KVQ_OK or a negative KVQ_ERR_* code; kvq_last_error() gives a thread-local message;
+ *   - matrices are row-major fp32: z is (N, D), the codebook E is (K, D); indices are int64;
+ *   - there is no CPU fallback: a device that is not compute capability 10.x yields KVQ_ERR_UNSUPPORTED.
+ */
+#ifndef KVQ_H_
+#define KVQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* kvq_stream_t; /* cudaStream_t */
+
+enum {
+  KVQ_OK = 0,
+  KVQ_ERR_ARG = -1,         /* null pointer / negative size */
+  KVQ_ERR_SHAPE = -2,       /* unsupported shape (D % 4 != 0, K > 2^31-1, ...) */
+  KVQ_ERR_WORKSPACE = -3,   /* workspace too small or misaligned */
+  KVQ_ERR_CUDA = -4,        /* a CUDA runtime / driver call failed */
+  KVQ_ERR_UNSUPPORTED = -5  /* not an sm_100 device, or mode not available for this shape */
+};
+
+/* Search precision (argument `mode`). */
+enum {
+  KVQ_SEARCH_AUTO = 0,  /* tf32 tensor-core search when the shape allows (D % 32 == 0), else fp32 */
+  KVQ_SEARCH_TF32 = 1,  /* TMA-fed tcgen05.mma.kind::tf32, fp32 accumulate in TMEM, fused argmin epilogue */
+  KVQ_SEARCH_FP32 = 2   /* CUDA-core fp32 FMA search (exact-precision mode, any D % 4 == 0) */
+};
+
+int kvq_version(void);
+const char* kvq_last_error(void);
+
+/* Device facts the host side needs for grid sizing / reporting. */
+int kvq_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Bytes of device workspace kvq_forward / kvq_backward / kvq_search need for this shape (256-B aligned). */
+size_t kvq_workspace_bytes(int64_t N, int D, int64_t K);
+
+/* |E_k|^2 for every code.  Replaces VectorQuantizer.py:60  torch.sum(weight**2, dim=1).
+ * e2 has room for K_pad >= K floats; entries [K, K_pad) are set to +inf (they mask padded tile columns). */
+int kvq_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, kvq_stream_t stream);
+
+/* Fused distance + argmin.  Replaces VectorQuantizer.py:59-65 (distance matrix + torch.argmin) without ever
+ * writing the N x K matrix.  score(i,k) = |E_k|^2 - 2 z_i . E_k  (the row-constant |z_i|^2 is dropped);
+ * the winner is the lowest score, ties to the lowest index, like torch.argmin.
+ *   idx   (N int64, may be NULL): k_offset + argmin_k
+ *   keys  (N int64, may be NULL): packed (orderable(score) << 32 | index); signed int64 order == (score, index)
+ *         lexicographic order, so shards combine with an element-wise MIN (used by the K-sharded codebook).
+ *         If `keys_accumulate` != 0 the kernel MIN-combines into the existing contents (atomicMin) instead
+ *         of overwriting, so several shards / calls can share one buffer.
+ * E is the local shard (K rows); k_offset is the global index of its first row. */
+int kvq_search(const float* z, const float* E, int64_t N, int D, int64_t K, int64_t k_offset, int mode,
+               int64_t* idx, int64_t* keys, int keys_accumulate,
+               void* workspace, size_t workspace_bytes, kvq_stream_t stream);
+
+/* Host helper: the packed key kvq_search emits for (score, index).  Signed int64 comparison of two keys orders
+ * them by score first (IEEE order, -0 == +0) and by index second. */
+int64_t kvq_pack_key(float score, uint32_t index);
+
+/* idx[i] = keys[i] & 0xffffffff  (after a cross-shard MIN of the packed keys). */
+int kvq_keys_to_idx(const int64_t* keys, int64_t N, int64_t* idx, kvq_stream_t stream);
+
+/* Codebook gather + straight-through + loss partial + usage histogram, one pass over z.
+ * Replaces VectorQuantizer.py:67-72 (one-hot, one-hot GEMM), :80 (z + (z_q - z).detach()), the reductions of
+ * :76-77 and the column mean of :84.
+ *   z_q[i]   = z[i] + (E[idx[i]-k_offset] - z[i])                (fp32, same rounding as the reference)
+ *   sq_sum  += sum_i sum_j (E[idx[i]] - z[i])_j^2                (double, accumulated: zero it first)
+ *   hist[k] += #{i : idx[i] == k_offset + k}                     (int32, accumulated: zero it first)
+ * Rows whose idx lies outside [k_offset, k_offset + K) are skipped (K-sharded codebook: another rank owns them);
+ * when `zero_skipped` != 0 their z_q rows are written as zeros so that a SUM across shards assembles z_q. */
+int kvq_quantize(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int64_t K,
+                 int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist,
+                 kvq_stream_t stream);
+
+/* loss = m + beta*m with m = sq_sum / (n_global*D)   (VectorQuantizer.py:76-77, value)
+ * perplexity = exp(-sum_k p_k log(p_k + 1e-10)), p_k = hist[k] / n_global   (VectorQuantizer.py:84-85) */
+int kvq_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, int D, int64_t K, float beta,
+                 float* loss, float* perplexity, kvq_stream_t stream);
+
+/* Whole forward of the layer: norms -> search -> quantize -> finalize.  VectorQuantizer.py:52-93.
+ * Outputs: z_q (N,D), idx (N int64), loss (1), perplexity (1), hist (K int32, the code-usage counts that the
+ * backward reuses for its segmented scatter-add). */
+int kvq_forward(const float* z, const float* E, int64_t N, int D, int64_t K, float beta, int mode,
+                float* z_q, int64_t* idx, float* loss, float* perplexity, int32_t* hist,
+                void* workspace, size_t workspace_bytes, kvq_stream_t stream);
+
+/* Backward of the layer (what autograd derives from VectorQuantizer.py:72-80):
+ *   dz[i]  = g_zq[i] + g_loss * 2 (z_i - q_i) / (n_global D)
+ *   dE[k]  = g_loss * beta * 2 / (n_global D) * sum_{i: idx_i = k} (q_i - z_i)      dense, exact zeros elsewhere
+ * g_zq may be NULL (no upstream gradient on z_q), g_loss may be NULL (loss unused; treated as 0),
+ * dz may be NULL (encoder frozen, "vq-ft" mode), dE may be NULL.  g_loss is a DEVICE scalar.
+ * `hist` is the histogram the forward produced (local to [k_offset, k_offset+K)). */
+int kvq_backward(const float* z, const float* E, const int64_t* idx, const int32_t* hist,
+                 const float* g_zq, const float* g_loss, int64_t N, int D, int64_t K, int64_t k_offset,
+                 float beta, int64_t n_global, float* dz, float* dE,
+                 void* workspace, size_t workspace_bytes, kvq_stream_t stream);
+
+/* dz from an assembled z_q (K-sharded codebook, where the winning codebook rows live on other ranks):
+ *   dz = g_zq + g_loss * 2 (z - z_q) / (n_global D).   Same autograd term as kvq_backward's dz. */
+int kvq_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t N, int D,
+                   int64_t n_global, float* dz, kvq_stream_t stream);
+
+/* Dense one-hot `min_encodings` (N,K) fp32.  VectorQuantizer.py:67-68.  Only on request: 4*N*K bytes. */
+int kvq_onehot(const int64_t* idx, int64_t N, int64_t K, float* out, kvq_stream_t stream);
+
+/* Token accuracy.  common/metrics.py:8-36.  a, b are (B,S) int64; acc is 1 float, per_sentence is B floats. */
+int kvq_seq_acc(const int64_t* a, const int64_t* b, int64_t B, int64_t S, float* acc, float* per_sentence,
+                kvq_stream_t stream);
+
+/* Token-id corruption helpers.  common/tensor_utils.py:13-49 and :52-87, with a counter-based device RNG
+ * (seeded; the reference uses the host RNG, so parity is distributional: exact counts, value ranges).
+ *  - replace: exactly floor(numel*pct) positions (a seeded random subset) receive uniform ints in [low, high).
+ *  - change_columns: floor(size(dim)*pct) randomly chosen slices along dim (0 or 1) of a (R,C) matrix are
+ *    overwritten, each with one random int in [low, high). */
+int kvq_replace_pct_rand_values(const int64_t* in, int64_t numel, double pct, int64_t low, int64_t high,
+                                uint64_t seed, int64_t* out, kvq_stream_t stream);
+int kvq_change_percentage_of_elements(const int64_t* in, int64_t R, int64_t C, int dim, double pct,
+                                      int64_t low, int64_t high, uint64_t seed, int64_t* out,
+                                      kvq_stream_t stream);
+
+/* End-to-end forward+backward with HOST buffers (pinned memory recommended): copies z and g_zq to the device
+ * in row chunks, runs the layer, and copies z_q, idx, dz, loss, perplexity and dE back, overlapping copies with
+ * compute on internal streams.  Synchronous: returns when every output is in host memory.
+ * g_loss_host is the host scalar weight of the loss in the total objective. */
+int kvq_forward_backward_host(const float* z_host, const float* E_host, const float* g_zq_host, float g_loss_host,
+                              int64_t N, int D, int64_t K, float beta, int mode,
+                              float* z_q_host, int64_t* idx_host, float* loss_host, float* perplexity_host,
+                              float* dz_host, float* dE_host, int64_t rows_per_chunk);
+/* Frees the device staging buffers kvq_forward_backward_host caches between calls. */
+int kvq_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVQ_H_ */

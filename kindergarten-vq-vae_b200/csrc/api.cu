@@ -1,0 +1,214 @@
+// extern "C" surface of libkvq.so (declared in include/kvq.h).  Argument checking, workspace carving and the
+// forward / backward orchestration live here; kernels live in the other translation units.
+#include <stdarg.h>
+
+#include "kvq_common.cuh"
+
+namespace kvq {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return KVQ_ERR_CUDA;
+}
+
+struct DevInfo { int sms = 0, major = 0, minor = 0; bool ok = false; };
+static DevInfo query_device() {
+  DevInfo d;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return d;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return d;
+  d.sms = prop.multiProcessorCount; d.major = prop.major; d.minor = prop.minor; d.ok = true;
+  return d;
+}
+static const DevInfo& device() {
+  static thread_local DevInfo d;
+  static thread_local int cached_dev = -1;
+  int dev = -2;
+  cudaGetDevice(&dev);
+  if (!d.ok || dev != cached_dev) { d = query_device(); cached_dev = dev; }
+  return d;
+}
+int sm_count() { const DevInfo& d = device(); return d.ok && d.sms > 0 ? d.sms : 148; }
+int check_device() {
+  const DevInfo& d = device();
+  KVQ_REQUIRE(d.ok, KVQ_ERR_CUDA, "no CUDA device available (libkvq has no CPU fallback)");
+  KVQ_REQUIRE(d.major == 10, KVQ_ERR_UNSUPPORTED, "libkvq is built for sm_100a only; device is sm_%d%d", d.major, d.minor);
+  return KVQ_OK;
+}
+
+static inline int64_t pad_codes(int64_t K) { return (K + SEARCH_TILE_N - 1) / SEARCH_TILE_N * SEARCH_TILE_N; }
+
+struct FwdWs { float* e2; long long* keys; double* sq_sum; size_t bytes; };
+static FwdWs carve_forward(void* ws, int64_t N, int64_t K) {
+  FwdWs w;
+  char* p = static_cast<char*>(ws);
+  size_t off = 0;
+  w.e2 = reinterpret_cast<float*>(p + off);      off += align_up((size_t)pad_codes(K) * 4, 256);
+  w.keys = reinterpret_cast<long long*>(p + off); off += align_up((size_t)(N > 0 ? N : 1) * 8, 256);
+  w.sq_sum = reinterpret_cast<double*>(p + off);  off += 256;
+  w.bytes = off;
+  return w;
+}
+
+static int check_shape(const char* who, int64_t N, int D, int64_t K) {
+  KVQ_REQUIRE(N >= 0 && K >= 1 && D >= 4, KVQ_ERR_ARG, "%s: bad sizes N=%lld D=%d K=%lld", who, (long long)N, D, (long long)K);
+  KVQ_REQUIRE(D % 4 == 0, KVQ_ERR_SHAPE, "%s: D=%d must be a multiple of 4 (128-bit accesses)", who, D);
+  KVQ_REQUIRE(D <= 1024, KVQ_ERR_SHAPE, "%s: D=%d exceeds 1024", who, D);
+  KVQ_REQUIRE(K <= 0x7fffff00ll && N <= 0x7fffff00ll, KVQ_ERR_SHAPE, "%s: N/K exceed 2^31", who);
+  return KVQ_OK;
+}
+
+static int resolve_mode(int mode, int64_t N, int D, int64_t K, int* out) {
+  if (mode == KVQ_SEARCH_AUTO) { *out = tf32_shape_ok(N, D, K) ? KVQ_SEARCH_TF32 : KVQ_SEARCH_FP32; return KVQ_OK; }
+  if (mode == KVQ_SEARCH_TF32) {
+    KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (D=%d)", D);
+    *out = mode; return KVQ_OK;
+  }
+  KVQ_REQUIRE(mode == KVQ_SEARCH_FP32, KVQ_ERR_ARG, "unknown search mode %d", mode);
+  *out = mode;
+  return KVQ_OK;
+}
+
+}  // namespace kvq
+
+using namespace kvq;
+
+extern "C" {
+
+int kvq_version(void) { return 100; }
+const char* kvq_last_error(void) { return g_err; }
+
+int kvq_device_info(int* sms, int* major, int* minor) {
+  const DevInfo& d = device();
+  KVQ_REQUIRE(d.ok, KVQ_ERR_CUDA, "no CUDA device available");
+  if (sms) *sms = d.sms;
+  if (major) *major = d.major;
+  if (minor) *minor = d.minor;
+  return KVQ_OK;
+}
+
+size_t kvq_workspace_bytes(int64_t N, int D, int64_t K) {
+  (void)D;
+  if (N < 0 || K < 1) return 0;
+  FwdWs w = carve_forward(nullptr, N, K);
+  const size_t b = backward_workspace_bytes(N, K);
+  return (w.bytes > b ? w.bytes : b) + 256;
+}
+
+int kvq_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  KVQ_REQUIRE(E && e2 && K_pad >= K, KVQ_ERR_ARG, "kvq_code_norms: null pointer or K_pad < K");
+  rc = check_shape("kvq_code_norms", 0, D, K); if (rc) return rc;
+  return launch_code_norms(E, K, D, e2, K_pad, (cudaStream_t)stream);
+}
+
+int kvq_search(const float* z, const float* E, int64_t N, int D, int64_t K, int64_t k_offset, int mode,
+               int64_t* idx, int64_t* keys, int keys_accumulate, void* ws, size_t ws_bytes, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  rc = check_shape("kvq_search", N, D, K); if (rc) return rc;
+  KVQ_REQUIRE(z && E && ws, KVQ_ERR_ARG, "kvq_search: null pointer");
+  KVQ_REQUIRE(idx || keys, KVQ_ERR_ARG, "kvq_search: need idx or keys");
+  KVQ_REQUIRE(k_offset >= 0 && k_offset + K <= 0xffffffffll, KVQ_ERR_SHAPE, "kvq_search: k_offset + K exceeds 2^32");
+  KVQ_REQUIRE(((uintptr_t)ws & 255) == 0, KVQ_ERR_WORKSPACE, "kvq_search: workspace must be 256-byte aligned");
+  FwdWs w = carve_forward(ws, N, K);
+  KVQ_REQUIRE(ws_bytes >= w.bytes, KVQ_ERR_WORKSPACE, "kvq_search: workspace %zu < %zu bytes", ws_bytes, w.bytes);
+  KVQ_REQUIRE(!keys_accumulate || keys, KVQ_ERR_ARG, "kvq_search: keys_accumulate needs keys");
+  int m; rc = resolve_mode(mode, N, D, K, &m); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); if (rc) return rc;
+  long long* kbuf = keys ? reinterpret_cast<long long*>(keys) : w.keys;  // internal keys only for split searches
+  if (m == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
+  return launch_search_fp32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
+}
+
+int64_t kvq_pack_key(float score, uint32_t index) { return (int64_t)pack_key(score, index); }
+
+int kvq_keys_to_idx(const int64_t* keys, int64_t N, int64_t* idx, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  KVQ_REQUIRE(keys && idx && N >= 0, KVQ_ERR_ARG, "kvq_keys_to_idx: bad arguments");
+  return launch_keys_to_idx(reinterpret_cast<const long long*>(keys), N, idx, (cudaStream_t)stream);
+}
+
+int kvq_quantize(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int64_t K, int64_t k_offset,
+                 int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  rc = check_shape("kvq_quantize", N, D, K); if (rc) return rc;
+  KVQ_REQUIRE(z && E && idx && z_q && sq_sum && hist, KVQ_ERR_ARG, "kvq_quantize: null pointer");
+  return launch_quantize(z, E, idx, N, D, K, k_offset, zero_skipped, z_q, sq_sum, hist, (cudaStream_t)stream);
+}
+
+int kvq_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, int D, int64_t K, float beta, float* loss,
+                 float* perplexity, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  KVQ_REQUIRE(sq_sum && hist && loss && perplexity && n_global > 0 && D > 0 && K > 0, KVQ_ERR_ARG,
+              "kvq_finalize: bad arguments");
+  return launch_finalize(sq_sum, hist, n_global, D, K, beta, loss, perplexity, (cudaStream_t)stream);
+}
+
+int kvq_forward(const float* z, const float* E, int64_t N, int D, int64_t K, float beta, int mode, float* z_q,
+                int64_t* idx, float* loss, float* perplexity, int32_t* hist, void* ws, size_t ws_bytes,
+                kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  rc = check_shape("kvq_forward", N, D, K); if (rc) return rc;
+  KVQ_REQUIRE(N >= 1, KVQ_ERR_ARG, "kvq_forward: N must be >= 1");
+  KVQ_REQUIRE(z && E && z_q && idx && loss && perplexity && hist && ws, KVQ_ERR_ARG, "kvq_forward: null pointer");
+  KVQ_REQUIRE(((uintptr_t)ws & 255) == 0, KVQ_ERR_WORKSPACE, "kvq_forward: workspace must be 256-byte aligned");
+  FwdWs w = carve_forward(ws, N, K);
+  KVQ_REQUIRE(ws_bytes >= w.bytes, KVQ_ERR_WORKSPACE, "kvq_forward: workspace %zu < %zu bytes", ws_bytes, w.bytes);
+  int m; rc = resolve_mode(mode, N, D, K, &m); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); if (rc) return rc;
+  if (m == KVQ_SEARCH_TF32) rc = launch_search_tf32(z, E, w.e2, N, D, K, 0, idx, w.keys, 0, st);
+  else rc = launch_search_fp32(z, E, w.e2, N, D, K, 0, idx, w.keys, 0, st);
+  if (rc) return rc;
+  KVQ_CUDA(cudaMemsetAsync(w.sq_sum, 0, sizeof(double), st));
+  KVQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int32_t), st));
+  rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, w.sq_sum, hist, st); if (rc) return rc;
+  return launch_finalize(w.sq_sum, hist, N, D, K, beta, loss, perplexity, st);
+}
+
+int kvq_backward(const float* z, const float* E, const int64_t* idx, const int32_t* hist, const float* g_zq,
+                 const float* g_loss, int64_t N, int D, int64_t K, int64_t k_offset, float beta, int64_t n_global,
+                 float* dz, float* dE, void* ws, size_t ws_bytes, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  rc = check_shape("kvq_backward", N, D, K); if (rc) return rc;
+  KVQ_REQUIRE(z && E && idx, KVQ_ERR_ARG, "kvq_backward: null pointer");
+  KVQ_REQUIRE(!dE || (hist && ws), KVQ_ERR_ARG, "kvq_backward: dE needs the forward histogram and a workspace");
+  KVQ_REQUIRE(n_global >= N && n_global > 0, KVQ_ERR_ARG, "kvq_backward: n_global must be >= N");
+  KVQ_REQUIRE(!ws || ((uintptr_t)ws & 255) == 0, KVQ_ERR_WORKSPACE, "kvq_backward: workspace must be 256-byte aligned");
+  return launch_backward(z, E, idx, hist, g_zq, g_loss, N, D, K, k_offset, beta, n_global, dz, dE, ws, ws_bytes,
+                         (cudaStream_t)stream);
+}
+
+int kvq_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t N, int D,
+                   int64_t n_global, float* dz, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  KVQ_REQUIRE(z && z_q && dz && N >= 0 && D >= 4 && D % 4 == 0 && n_global >= N && n_global > 0, KVQ_ERR_ARG,
+              "kvq_dz_from_zq: bad arguments");
+  return launch_dz_from_zq(z, z_q, g_zq, g_loss, N * D, 1.0 / ((double)n_global * (double)D), dz, (cudaStream_t)stream);
+}
+
+int kvq_onehot(const int64_t* idx, int64_t N, int64_t K, float* out, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  KVQ_REQUIRE(idx && out && N >= 0 && K >= 1, KVQ_ERR_ARG, "kvq_onehot: bad arguments");
+  return launch_onehot(idx, N, K, out, (cudaStream_t)stream);
+}
+
+int kvq_seq_acc(const int64_t* a, const int64_t* b, int64_t B, int64_t S, float* acc, float* per, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  KVQ_REQUIRE(a && b && acc && per && B >= 0 && S >= 0, KVQ_ERR_ARG, "kvq_seq_acc: bad arguments");
+  KVQ_REQUIRE(B * S < (1ll << 32), KVQ_ERR_SHAPE, "kvq_seq_acc: more than 2^32 tokens");
+  return launch_seq_acc(a, b, B, S, acc, per, (cudaStream_t)stream);
+}
+
+}  // extern "C"

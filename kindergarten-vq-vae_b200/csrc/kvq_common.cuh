@@ -1,0 +1,106 @@
+// Shared device/host helpers for libkvq (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/kvq.h"
+
+namespace kvq {
+
+// ---- thread-local error text -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define KVQ_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (call);                                                        \
+    if (_e != cudaSuccess) return ::kvq::cuda_fail(_e, #call, __FILE__, __LINE__);   \
+  } while (0)
+
+#define KVQ_LAUNCH_CHECK() KVQ_CUDA(cudaGetLastError())
+
+#define KVQ_REQUIRE(cond, code, ...)        \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::kvq::set_error(__VA_ARGS__);        \
+      return (code);                        \
+    }                                       \
+  } while (0)
+
+int sm_count();          // cached, current device
+int check_device();      // KVQ_OK iff compute capability 10.x
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int64_t min_i64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// ---- packed (score, index) keys ----------------------------------------------------------------
+// Signed-int64 order of the key == lexicographic (score, index) order, so an element-wise MIN (atomicMin on
+// the device, ncclMin across GPUs) is an argmin with torch's lowest-index tie-break.
+__host__ __device__ __forceinline__ long long pack_key(float score, uint32_t index) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(score + 0.0f);  // +0.0f folds -0.0 into +0.0 (they compare equal as floats)
+#else
+  float s = score + 0.0f;
+  uint32_t u;
+  memcpy(&u, &s, 4);
+#endif
+  // float order -> signed 32-bit order: negative floats flip all non-sign bits.
+  int32_t o = (int32_t)(u ^ ((uint32_t)((int32_t)u >> 31) & 0x7fffffffu));
+  return (long long)(((unsigned long long)(uint32_t)o << 32) | (unsigned long long)index);
+}
+__host__ __device__ __forceinline__ uint32_t key_index(long long key) { return (uint32_t)((unsigned long long)key & 0xffffffffull); }
+
+constexpr long long KEY_INIT = 0x7fffffffffffffffll;
+
+// ---- small device utilities ----------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 128-bit streaming global accesses (data touched once: keep it out of L1).
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- kernels' host launchers (one per translation unit) --------------------------------------------
+int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st);
+int launch_search_fp32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
+                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st);
+int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
+                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st);
+bool tf32_shape_ok(int64_t N, int D, int64_t K);
+int launch_fill_keys(long long* keys, int64_t N, cudaStream_t st);
+int launch_keys_to_idx(const long long* keys, int64_t N, int64_t* idx, cudaStream_t st);
+int launch_quantize(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int64_t K,
+                    int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st);
+int launch_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, int D, int64_t K, float beta,
+                    float* loss, float* perplexity, cudaStream_t st);
+int launch_backward(const float* z, const float* E, const int64_t* idx, const int32_t* hist, const float* g_zq,
+                    const float* g_loss, int64_t N, int D, int64_t K, int64_t k_offset, float beta,
+                    int64_t n_global, float* dz, float* dE, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t backward_workspace_bytes(int64_t N, int64_t K);
+int launch_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t numel,
+                      double inv_nd, float* dz, cudaStream_t st);
+int launch_onehot(const int64_t* idx, int64_t N, int64_t K, float* out, cudaStream_t st);
+int launch_seq_acc(const int64_t* a, const int64_t* b, int64_t B, int64_t S, float* acc, float* per, cudaStream_t st);
+
+constexpr int SEARCH_TILE_N = 256;  // e2 is padded to a multiple of this (tensor-core tile width)
+
+}  // namespace kvq

@@ -1,0 +1,442 @@
+// Tensor-core distance + argmin for sm_100a: TMA -> shared memory -> tcgen05.mma.kind::tf32 -> TMEM -> fused
+// argmin epilogue.  Replaces models/shelgon3/VectorQuantizer.py:59-65; the N x K distance matrix lives only in
+// TMEM, 128 x 256 fp32 at a time, and never reaches shared or global memory.
+//
+//   score(i,k) = |E_k|^2 - 2 z_i . E_k          (tf32 products, fp32 accumulate; |z_i|^2 is row-constant)
+//   idx[i]     = argmin_k score(i,k), ties -> lowest k
+//
+// Work decomposition.  An "item" is one tile of 128 latents swept over a range of 256-code tiles; a persistent
+// CTA (one per SM) takes items round-robin.  For D <= 256 the latent tile (128 x D fp32, <= 128 KB) is loaded
+// once per item and stays resident in shared memory while codebook tiles stream through a ring of 32 KB stages,
+// so the only steady-state operand traffic is the codebook (L2 resident).  For larger D both operands stream.
+//
+// Warp roles (320 threads):  warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..9 = epilogue.  The accumulator is double buffered in TMEM (2 x 256 columns = all 512), so the argmin
+// epilogue of code tile j overlaps the MMAs of tile j+1.  Epilogue warp w reads TMEM lanes 32*(w%4).. (its
+// hardware lane quarter) and one half of the 256 columns; each thread owns one latent row and keeps four
+// independent running (min, index) chains.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime, no -lcuda needed)
+
+#include "kvq_common.cuh"
+
+namespace kvq {
+
+namespace t5 {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 32;                         // fp32 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 8;                           // tf32
+constexpr int A_KBLOCK_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 4;   // 32 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;   // 320
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 232448;                  // 227 KB opt-in maximum per CTA
+constexpr int SMEM_CTRL_BYTES = 1024 + 1024;        // barriers + tmem slot | cross-half merge scratch
+constexpr int RESIDENT_MAX_D = 256;
+
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor bit layout): c_format F32 @4, a/b_format TF32 @7/@10,
+// a/b K-major (bits 15/16 = 0), n_dim = N>>3 @17, m_dim = M>>4 @24.
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                           ((uint32_t)(BLOCK_M >> 4) << 24);
+
+struct Params {
+  int64_t N, K, k_offset;
+  int D;
+  int num_kblocks;      // D / 32
+  int n_tiles;          // ceil(K / 256)
+  int tiles_per_split;  // code tiles per item
+  int ksplit;
+  int64_t m_tiles;
+  int64_t n_items;      // m_tiles * ksplit
+  int resident;         // latent tile resident in smem
+  int stages;
+  int use_atomic;       // MIN-combine into keys (split code range or caller-accumulated keys)
+  const float* e2;      // padded to n_tiles*256 with +inf
+  int64_t* idx;
+  long long* keys;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Spin with a watchdog: a protocol bug traps (the launch reports an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (((++spins) & 0xfffu) == 0 && clock64() - t0 > 20000000000ll) {  // ~10 s at 2 GHz
+      printf("kvq tf32 search: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  uint64_t d = (uint64_t)((addr & 0x3ffffu) >> 4);   // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset = 1024 B, bits [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B
+  return d;
+}
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread, then wait for the load.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
+                   const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128-byte swizzle atoms (8 rows x 128 B).
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // shared-memory map: [control 2 KB][resident latent tile (resident mode)][stage ring]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t bar_full = base;                      // [MAX_STAGES]
+  const uint32_t bar_empty = base + 8 * MAX_STAGES;    // [MAX_STAGES]
+  const uint32_t bar_a_full = base + 16 * MAX_STAGES;
+  const uint32_t bar_a_empty = bar_a_full + 8;
+  const uint32_t bar_tm_full = bar_a_empty + 8;        // [2]
+  const uint32_t bar_tm_empty = bar_tm_full + 16;      // [2]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 16 * MAX_STAGES + 48);
+  float* merge_val = reinterpret_cast<float*>(smem + 1024);
+  uint32_t* merge_idx = reinterpret_cast<uint32_t*>(smem + 1024 + 512);
+  (void)bars;
+
+  const uint32_t a_bytes = p.resident ? (uint32_t)p.num_kblocks * A_KBLOCK_BYTES : 0u;
+  const uint32_t a_region = base + SMEM_CTRL_BYTES;
+  const uint32_t ring = a_region + a_bytes;
+  const uint32_t stage_bytes = p.resident ? B_STAGE_BYTES : (A_KBLOCK_BYTES + B_STAGE_BYTES);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_empty, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tm_full + 8 * a, 1);
+      mbar_init(bar_tm_empty + 8 * a, NUM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // one warp allocates all 512 TMEM columns (two 128 x 256 fp32 accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_z) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_e) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0;
+      for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int64_t m_tile = item / p.ksplit;
+        const int ks = (int)(item % p.ksplit);
+        const int m0 = (int)(m_tile * BLOCK_M);
+        const int t_begin = ks * p.tiles_per_split;
+        const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+        if (p.resident) {
+          mbar_wait(bar_a_empty, a_phase ^ 1);          // previous item's MMAs have finished reading the tile
+          mbar_expect_tx(bar_a_full, a_bytes);
+          for (int kb = 0; kb < p.num_kblocks; ++kb)
+            tma_load_2d(a_region + kb * A_KBLOCK_BYTES, &tmap_z, kb * BLOCK_K, m0, bar_a_full);
+          a_phase ^= 1;
+        }
+        for (int t = t_begin; t < t_end; ++t) {
+          const int n0 = t * BLOCK_N;
+          for (int kb = 0; kb < p.num_kblocks; ++kb) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t sbase = ring + stage * stage_bytes;
+            mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
+            if (!p.resident) {
+              tma_load_2d(sbase, &tmap_z, kb * BLOCK_K, m0, bar_full + 8 * stage);
+              tma_load_2d(sbase + A_KBLOCK_BYTES, &tmap_e, kb * BLOCK_K, n0, bar_full + 8 * stage);
+            } else {
+              tma_load_2d(sbase, &tmap_e, kb * BLOCK_K, n0, bar_full + 8 * stage);
+            }
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+      for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int ks = (int)(item % p.ksplit);
+        const int t_begin = ks * p.tiles_per_split;
+        const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+        if (p.resident) {
+          mbar_wait(bar_a_full, a_phase);
+          a_phase ^= 1;
+          tc_fence_after();
+        }
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(bar_tm_empty + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          for (int kb = 0; kb < p.num_kblocks; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sbase = ring + stage * stage_bytes;
+            const uint32_t a_addr = p.resident ? (a_region + kb * A_KBLOCK_BYTES) : sbase;
+            const uint32_t b_addr = p.resident ? sbase : (sbase + A_KBLOCK_BYTES);
+            const uint64_t adesc = smem_desc(a_addr);
+            const uint64_t bdesc = smem_desc(b_addr);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+              tc_mma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(bar_empty + 8 * stage);                 // stage reusable once these MMAs retire
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(bar_tm_full + 8 * acc);                   // accumulator complete -> epilogue
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        if (p.resident) tc_commit(bar_a_empty);               // latent tile may be overwritten
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== argmin epilogue ===========================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;            // which 128 of the 256 accumulator columns
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int64_t m_tile = item / p.ksplit;
+      const int ks = (int)(item % p.ksplit);
+      const int t_begin = ks * p.tiles_per_split;
+      const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+      float best[4];
+      uint32_t bidx[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { best[c] = INFINITY; bidx[c] = (uint32_t)(t_begin * BLOCK_N + half * 128 + c); }
+
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(bar_tm_full + 8 * acc, acc_phase);
+        tc_fence_after();
+        const uint32_t col0 = (uint32_t)(t * BLOCK_N + half * 128);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * 128;
+        const float4* e2v = reinterpret_cast<const float4*>(p.e2 + col0);
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {
+          uint32_t r[32];
+          tmem_ld32(taddr + b * 32, r);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 en = __ldg(e2v + b * 8 + j4);
+            const float e[4] = {en.x, en.y, en.z, en.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float s = fmaf(-2.f, __uint_as_float(r[j4 * 4 + c]), e[c]);
+              if (s < best[c]) { best[c] = s; bidx[c] = col0 + b * 32 + j4 * 4 + c; }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tm_empty + 8 * acc);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      // merge the four chains (lexicographic (score, index): lowest index wins ties)
+      float bv = best[0];
+      uint32_t bi = bidx[0];
+#pragma unroll
+      for (int c = 1; c < 4; ++c)
+        if (best[c] < bv || (best[c] == bv && bidx[c] < bi)) { bv = best[c]; bi = bidx[c]; }
+      // merge the two column halves through shared memory
+      if (half == 1) { merge_val[row_in_tile] = bv; merge_idx[row_in_tile] = bi; }
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+      if (half == 0) {
+        const float ov = merge_val[row_in_tile];
+        const uint32_t oi = merge_idx[row_in_tile];
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        const int64_t row = m_tile * BLOCK_M + row_in_tile;
+        if (row < p.N) {
+          const uint32_t gi = (uint32_t)(bi + p.k_offset);
+          const long long key = pack_key(bv, gi);
+          if (p.use_atomic) {
+            atomicMin(p.keys + row, key);
+          } else {
+            if (p.keys) p.keys[row] = key;
+            if (p.idx) p.idx[row] = (int64_t)gi;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || !sym)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// 2-D row-major fp32 matrix (rows x D), box = box_rows x 32 floats, 128-byte swizzle, OOB rows read as zero.
+static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int D, int box_rows, bool round_tf32) {
+  EncodeTiledFn enc = get_encoder();
+  KVQ_REQUIRE(enc, KVQ_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)D * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, round_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KVQ_REQUIRE(r == CUDA_SUCCESS, KVQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld D=%d", (int)r,
+              (long long)rows, D);
+  return KVQ_OK;
+}
+
+}  // namespace t5
+
+bool tf32_shape_ok(int64_t N, int D, int64_t K) {
+  return N > 0 && K > 0 && D >= 32 && D % 32 == 0 && D <= 4096 && N < (1ll << 31) - 256 && K < (1ll << 31) - 256;
+}
+
+int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
+                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st) {
+  using namespace t5;
+  if (N <= 0) return KVQ_OK;
+  KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (got N=%lld D=%d K=%lld)",
+              (long long)N, D, (long long)K);
+  KVQ_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)E & 15) == 0, KVQ_ERR_ARG,
+              "tf32 search needs 16-byte aligned z and E (TMA)");
+
+  Params p;
+  p.N = N; p.K = K; p.k_offset = k_offset; p.D = D;
+  p.num_kblocks = D / BLOCK_K;
+  p.n_tiles = (int)((K + BLOCK_N - 1) / BLOCK_N);
+  p.m_tiles = (N + BLOCK_M - 1) / BLOCK_M;
+  const int sms = sm_count();
+  int ksplit = 1;
+  if (p.m_tiles < sms) ksplit = (int)min_i64(p.n_tiles, (sms + p.m_tiles - 1) / p.m_tiles);
+  p.tiles_per_split = (p.n_tiles + ksplit - 1) / ksplit;
+  p.ksplit = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.n_items = p.m_tiles * p.ksplit;
+  p.resident = (D <= RESIDENT_MAX_D) ? 1 : 0;
+  const int a_bytes = p.resident ? p.num_kblocks * A_KBLOCK_BYTES : 0;
+  const int stage_bytes = p.resident ? B_STAGE_BYTES : (A_KBLOCK_BYTES + B_STAGE_BYTES);
+  int stages = (SMEM_LIMIT - 1024 - SMEM_CTRL_BYTES - a_bytes) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  KVQ_REQUIRE(stages >= 2, KVQ_ERR_SHAPE, "tf32 search: no room for a 2-stage ring at D=%d", D);
+  p.stages = stages;
+  p.use_atomic = (p.ksplit > 1 || keys_accumulate) ? 1 : 0;
+  p.e2 = e2; p.idx = idx; p.keys = keys;
+  KVQ_REQUIRE(!p.use_atomic || keys, KVQ_ERR_ARG, "kvq_search(tf32): split/accumulate search needs a keys buffer");
+  const size_t smem = 1024 + SMEM_CTRL_BYTES + (size_t)a_bytes + (size_t)stages * stage_bytes;
+
+  static const bool round_tf32 = []() {
+    const char* e = getenv("KVQ_TMA_ROUND_TF32");
+    return e && e[0] == '1';
+  }();
+  CUtensorMap mz, me;
+  int rc = make_map(&mz, z, N, D, BLOCK_M, round_tf32);
+  if (rc) return rc;
+  rc = make_map(&me, E, K, D, BLOCK_N, round_tf32);
+  if (rc) return rc;
+
+  if (p.use_atomic && !keys_accumulate) {
+    rc = launch_fill_keys(keys, N, st);
+    if (rc) return rc;
+  }
+  KVQ_CUDA(cudaFuncSetAttribute(search_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)min_i64(p.n_items, sms);
+  search_tf32_kernel<<<grid, NUM_THREADS, smem, st>>>(mz, me, p);
+  KVQ_LAUNCH_CHECK();
+  if (p.use_atomic && idx && !keys_accumulate) return launch_keys_to_idx(keys, N, idx, st);
+  return KVQ_OK;
+}
+
+}  // namespace kvq

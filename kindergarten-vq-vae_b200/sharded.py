@@ -1,0 +1,204 @@
+"""Multi-GPU forms of the VQ layer (new capability: the reference is single-device).
+
+One process per GPU, `torch.distributed` (NCCL over NVLink / NVSwitch) for the exchange steps.  The path shards in
+exactly two natural ways, and each needs only reductions:
+
+* BatchShardedVectorQuantizer -- latents are sharded by rows, the codebook is replicated.  Local search, gather,
+  straight-through, dz and bucketed dE; then ONE exchange per direction:
+    forward : all-reduce(SUM) of [sum of squared residuals (f64), usage histogram (i32)]
+    backward: all-reduce(SUM) of the dense codebook gradient dE (K x D fp32)
+  Everything is normalised by the GLOBAL N*D so the result equals the reference on the concatenated batch.
+
+* CodebookShardedVectorQuantizer -- the codebook is sharded by rows (huge K), latents are replicated.  Each rank
+  searches its shard and emits packed (score, index) int64 keys; the cross-GPU argmin is
+    all-reduce(MIN) over the N keys   (signed order of the key == (score, index) order: lowest index wins ties)
+  then each rank gathers the rows it owns (zeros elsewhere) and z_q is assembled with an all-reduce(SUM); the
+  histogram shards are all-gathered for the perplexity.  The codebook gradient needs no communication at all:
+  every rank bucket-sums only the latents that chose one of its codes.
+
+The local compute steps come from a `backend` object (default: the CUDA functional module).  Tests inject a
+CPU stand-in there to exercise this orchestration under gloo without a GPU; the product never does.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+from torch import Tensor
+
+from . import functional as _cuda_backend
+from .vector_quantizer import ONEHOT_AUTO_BYTES
+
+
+def _world(group) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def _rank(group) -> int:
+    return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard_bounds(total: int, parts: int, part: int):
+    """Contiguous equal shards (the last may be short): [lo, hi) of shard `part`."""
+    per = (total + parts - 1) // parts
+    lo = min(part * per, total)
+    return lo, min(lo + per, total)
+
+
+# ------------------------------------------------------------------------------------------------
+# batch-sharded (data parallel)
+# ------------------------------------------------------------------------------------------------
+class _BatchShardedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, E, beta, mode, group, n_global, backend):
+        N, D = z.shape
+        idx, _ = backend.search(z, E, mode=mode)
+        z_q, sq_sum, hist_local = backend.quantize(z, E, idx)
+        hist = hist_local.clone()
+        if _world(group) > 1:
+            # two small reductions (8 B and 4K B); both are needed before the loss / perplexity exist
+            dist.all_reduce(sq_sum, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        loss, perplexity = backend.finalize(sq_sum, hist, n_global, D, beta)
+        loss, perplexity = loss.clone(), perplexity.clone()
+        ctx.save_for_backward(z, E, idx, hist_local)
+        ctx.beta, ctx.group, ctx.n_global, ctx.backend = beta, group, n_global, backend
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(perplexity, idx, hist)
+        return loss, z_q, perplexity, idx, hist
+
+    @staticmethod
+    def backward(ctx, g_loss, g_zq, *_):
+        z, E, idx, hist_local = ctx.saved_tensors
+        need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_zq is not None:
+            g_zq = g_zq.contiguous()
+        if g_loss is None:
+            dz = g_zq if need_dz else None
+            dE = torch.zeros_like(E) if need_dE else None
+        else:
+            g_loss = g_loss.detach().to(torch.float32).contiguous()
+            dz, dE = ctx.backend.vq_backward(z, E, idx, hist_local, ctx.beta, g_zq=g_zq, g_loss=g_loss,
+                                             need_dz=need_dz, need_dE=need_dE, n_global=ctx.n_global)
+        if need_dE and _world(ctx.group) > 1:
+            dist.all_reduce(dE, op=dist.ReduceOp.SUM, group=ctx.group)   # codebook gradient of the global batch
+        return dz, dE, None, None, None, None, None
+
+
+class BatchShardedVectorQuantizer(nn.Module):
+    """VectorQuantizer over a row-sharded batch; outputs equal the single-device layer on the concatenated batch.
+    Every rank must pass the same number of latents unless `n_global` is given to forward().  The codebook
+    gradient is all-reduced here -- do not also wrap `embedding.weight` in DistributedDataParallel."""
+
+    def __init__(self, n_e, e_dim, beta, vq_codebook_init_values: Tensor = None, *, process_group=None,
+                 search: str = "auto", min_encodings=False, backend=None):
+        super().__init__()
+        self.n_e, self.e_dim, self.beta = n_e, e_dim, beta
+        self.search, self.group = search, process_group
+        self.return_min_encodings = min_encodings
+        self.backend = backend if backend is not None else _cuda_backend
+        self.embedding = nn.Embedding(n_e, e_dim)
+        if vq_codebook_init_values is not None:
+            self.embedding.weight.data.copy_(vq_codebook_init_values)
+        else:
+            self.embedding.weight.data.uniform_(-1.0 / n_e, 1.0 / n_e)
+
+    @torch.compiler.disable
+    def forward(self, z: Tensor, device=None, n_global: Optional[int] = None):
+        batch_size, seq_len, _ = z.shape
+        zf = z.view((-1, self.e_dim))
+        if n_global is None:
+            n_global = zf.shape[0] * _world(self.group)
+        loss, z_q, perplexity, idx, _ = _BatchShardedFn.apply(zf, self.embedding.weight, float(self.beta),
+                                                               self.search, self.group, int(n_global), self.backend)
+        want = self.return_min_encodings
+        if want == "auto":
+            want = zf.shape[0] * self.n_e * 4 <= ONEHOT_AUTO_BYTES
+        onehot = self.backend.onehot(idx, self.n_e) if want else None
+        return loss, z_q.view(z.shape), perplexity, onehot, idx.reshape((batch_size, seq_len, 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# codebook-sharded (very large K)
+# ------------------------------------------------------------------------------------------------
+class _CodebookShardedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, E_local, beta, mode, group, k_offset, k_total, backend):
+        N, D = z.shape
+        world = _world(group)
+        _, keys = backend.search(z, E_local, mode=mode, k_offset=k_offset, want_idx=False, want_keys=True)
+        if world > 1:
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)      # cross-GPU (distance, index) argmin
+        idx = backend.keys_to_idx(keys)
+        z_q, sq_sum, hist_local = backend.quantize(z, E_local, idx, k_offset=k_offset, zero_skipped=True)
+        if world > 1:
+            dist.all_reduce(z_q, op=dist.ReduceOp.SUM, group=group)       # each row is non-zero on exactly one rank
+            dist.all_reduce(sq_sum, op=dist.ReduceOp.SUM, group=group)
+            per = E_local.shape[0]
+            parts = [torch.empty(per, dtype=hist_local.dtype, device=hist_local.device) for _ in range(world)]
+            dist.all_gather(parts, hist_local.contiguous(), group=group)
+            hist = torch.cat(parts)[:k_total].contiguous()
+        else:
+            hist = hist_local
+        loss, perplexity = backend.finalize(sq_sum, hist, N, D, beta)
+        loss, perplexity = loss.clone(), perplexity.clone()
+        ctx.save_for_backward(z, E_local, idx, hist_local, z_q)
+        ctx.beta, ctx.k_offset, ctx.backend = beta, k_offset, backend
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(perplexity, idx, hist)
+        return loss, z_q, perplexity, idx, hist
+
+    @staticmethod
+    def backward(ctx, g_loss, g_zq, *_):
+        z, E_local, idx, hist_local, z_q = ctx.saved_tensors
+        need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_zq is not None:
+            g_zq = g_zq.contiguous()
+        if g_loss is None:
+            return (g_zq if need_dz else None), (torch.zeros_like(E_local) if need_dE else None), None, None, None, \
+                None, None, None
+        g_loss = g_loss.detach().to(torch.float32).contiguous()
+        dz = ctx.backend.dz_from_zq(z, z_q, g_zq, g_loss, z.shape[0]) if need_dz else None
+        dE = None
+        if need_dE:   # local: only latents that chose one of this rank's codes contribute
+            _, dE = ctx.backend.vq_backward(z, E_local, idx, hist_local, ctx.beta, g_zq=None, g_loss=g_loss,
+                                            need_dz=False, need_dE=True, k_offset=ctx.k_offset)
+        return dz, dE, None, None, None, None, None, None
+
+
+class CodebookShardedVectorQuantizer(nn.Module):
+    """VectorQuantizer whose codebook rows are sharded over the ranks of `process_group` (latents replicated).
+    `embedding` holds only this rank's shard: rows [k_offset, k_offset + k_local) of the global (n_e, e_dim)
+    codebook (all shards have ceil(n_e / world) rows; the tail of the last one is padding that can never win)."""
+
+    def __init__(self, n_e, e_dim, beta, vq_codebook_init_values: Tensor = None, *, process_group=None,
+                 search: str = "auto", backend=None):
+        super().__init__()
+        self.n_e, self.e_dim, self.beta = n_e, e_dim, beta
+        self.search, self.group = search, process_group
+        self.backend = backend if backend is not None else _cuda_backend
+        world, rank = _world(process_group), _rank(process_group)
+        self.k_per = (n_e + world - 1) // world
+        self.k_offset = rank * self.k_per
+        lo, hi = shard_bounds(n_e, world, rank)
+        self.k_valid = hi - lo
+        self.embedding = nn.Embedding(self.k_per, e_dim)
+        with torch.no_grad():
+            if vq_codebook_init_values is not None:
+                self.embedding.weight[: self.k_valid].copy_(vq_codebook_init_values[lo:hi])
+            else:
+                g = torch.Generator().manual_seed(0x5EED + rank)
+                self.embedding.weight.copy_((torch.rand(self.k_per, e_dim, generator=g) * 2 - 1) / n_e)
+            if self.k_valid < self.k_per:
+                self.embedding.weight[self.k_valid:] = float("inf")   # padding rows: infinite distance
+
+    @torch.compiler.disable
+    def forward(self, z: Tensor, device=None):
+        batch_size, seq_len, _ = z.shape
+        zf = z.view((-1, self.e_dim))
+        loss, z_q, perplexity, idx, _ = _CodebookShardedFn.apply(zf, self.embedding.weight, float(self.beta),
+                                                                  self.search, self.group, self.k_offset, self.n_e,
+                                                                  self.backend)
+        return loss, z_q.view(z.shape), perplexity, None, idx.reshape((batch_size, seq_len, 1))

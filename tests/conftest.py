@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+def load_golden(name):
+    import numpy as np
+    import torch
+    d = np.load(os.path.join(GOLDEN, f"vq_{name}.npz"))
+    out = {}
+    for k in d.files:
+        v = d[k]
+        out[k] = torch.from_numpy(np.array(v))   # 0-d arrays become 0-d tensors
+    return out
+
+
+GOLDEN_CASES = ["small", "default", "bert", "ties", "wide"]

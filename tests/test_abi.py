@@ -1,0 +1,80 @@
+"""The C-ABI library loads on a CPU-only host and exports every symbol include/kvq.h declares.
+No compute entry point is exercised here (there is no GPU); argument validation and the loud failure are."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from kindergarten_vq_vae_b200 import _lib
+    return _lib.load()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "kvq.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kvq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    from kindergarten_vq_vae_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/kvq.h but not exported by libkvq.so"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(_lib.SIGNATURES) == declared
+
+
+def test_no_torch_types_in_abi():
+    text = open(os.path.join(ROOT, "include", "kvq.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)       # declarations only (comments cite the reference's torch calls)
+    assert "torch" not in code.lower() and "at::" not in code and "Tensor" not in code and "#include <cuda" not in code
+
+
+def test_version_and_workspace(lib):
+    assert lib.kvq_version() == 100
+    small = lib.kvq_workspace_bytes(4096, 768, 512)
+    big = lib.kvq_workspace_bytes(1 << 20, 256, 65536)
+    assert 0 < small < big
+    assert big >= (1 << 20) * 8        # room for one packed key / one bucket slot per latent
+    assert lib.kvq_workspace_bytes(-1, 256, 512) == 0
+
+
+def test_pack_key_orders_by_score_then_index(lib):
+    f = lambda s, i: lib.kvq_pack_key(ctypes.c_float(s), ctypes.c_uint32(i))
+    scores = [-float("inf"), -3.5e10, -1.0, -1e-38, 0.0, 1e-38, 0.5, 7e20, float("inf")]
+    keys = [f(s, 9) for s in scores]
+    assert keys == sorted(keys) and len(set(keys)) == len(keys)
+    assert f(1.25, 3) < f(1.25, 4) < f(1.25, 0xFFFFFFFF)      # same score: lower index wins
+    assert f(-0.0, 7) == f(0.0, 7)                             # -0 and +0 compare equal as floats
+    assert f(2.0, 0) > f(1.0, 0xFFFFFFFF)                      # score dominates index
+    assert f(1.0, 123456) & 0xFFFFFFFF == 123456
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_compute_entry_points_fail_loudly_without_gpu(lib):
+    assert lib.kvq_device_info(None, None, None) != 0
+    assert b"no CUDA device" in lib.kvq_last_error()
+    rc = lib.kvq_forward(None, None, 16, 32, 8, 0.25, 0, None, None, None, None, None, None, 0, None)
+    assert rc != 0 and len(lib.kvq_last_error()) > 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_module_refuses_cpu_tensors():
+    from kindergarten_vq_vae_b200 import VectorQuantizer, seq_acc, replace_pct_rand_values
+    vq = VectorQuantizer(n_e=16, e_dim=32, beta=0.25)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vq.forward(torch.randn(2, 4, 32), "cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        seq_acc(torch.zeros(2, 3, dtype=torch.long), torch.zeros(2, 3, dtype=torch.long))
+    with pytest.raises(RuntimeError):
+        replace_pct_rand_values(torch.zeros(2, 3, dtype=torch.long), 0.5, 0, 10)
