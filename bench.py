@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- VQ latents/sec (forward + backward) at K=65536, D=256 on N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl kvq|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch of synthetic latents: the drop-in VectorQuantizer's forward
+(code norms, fused tf32 distance+argmin, gather + straight-through + loss + histogram, loss/perplexity) and its
+backward (dz fused with the bucketed scatter-add into dE).  Workload: BASELINE.json's metric configuration --
+2^20 latents x 256 dims against a 65536-code book per GPU (weak scaling: batch-sharded latents, replicated
+codebook, codebook gradient + histogram + loss partial all-reduced over NCCL).
+
+One JSON line is printed by rank 0 (see README / DESIGN.md for the field meanings).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vq_latents_per_sec_fwd_bwd"
+UNIT = "latents/s"
+N_PER_GPU = 1 << 20
+D = 256
+K = 65536
+BETA = 0.25
+SEED = 69  # the reference's DS_GEN_SEED (common/consts.py:3)
+CPU_SAMPLE_ROWS = 4096
+
+
+def peaks():
+    """Roofline denominators: driver-measured numbers if present, else the profiling guide's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML, else nvidia-smi)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _reasons(self, mask: int):
+        n = self._nvml
+        table = [("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"),
+                 ("hw_power_brake", "nvmlClocksThrottleReasonHwPowerBrakeSlowdown")]
+        for name, attr in table:
+            bit = getattr(n, attr, None)
+            if bit is not None and mask & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        n = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self._reasons(mask)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self._nvml is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        if not self.samples:
+            return self._smi_once()
+        return dict(sm_mhz=statistics.median(self.samples), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(self.samples))
+
+    def _smi_once(self):
+        import subprocess
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            a, b = [float(x) for x in out.strip().split(",")]
+            return dict(sm_mhz=a, sm_max_mhz=b, reasons=[], samples=1, note="single idle nvidia-smi sample")
+        except Exception as exc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0, note=f"no clock source: {exc}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+def synth_device(torch, dev, n_rows, seed):
+    """Seeded synthetic inputs: z, g_zq ~ N(0,1); data-scale codebook = K latents + noise
+    (mirrors the reference's k-means init with minit='points', vq_codebook_init_weights.py:85)."""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    z = torch.randn(n_rows, D, device=dev, generator=gen)
+    gz = torch.randn(n_rows, D, device=dev, generator=gen)
+    gen_e = torch.Generator(device=dev).manual_seed(SEED)       # same codebook on every rank
+    base = torch.randn(K, D, device=dev, generator=gen_e)
+    E = base + 0.1 * torch.randn(K, D, device=dev, generator=gen_e)
+    return z, gz, E
+
+
+def cpu_reference_rate(torch, steps, warmup, rows):
+    """Literal CPU port of the reference step (oracle.vq_oracle.literal_step_cpu) on a bounded row sample."""
+    from oracle import vq_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(SEED)
+    z = torch.randn(rows // 64, 64, D, generator=gen)
+    gz = torch.randn(rows // 64, 64, D, generator=gen)
+    E = torch.randn(K, D, generator=gen) + 0.1 * torch.randn(K, D, generator=gen)
+    for _ in range(warmup):
+        O.literal_step_cpu(z, E, BETA, gz)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.literal_step_cpu(z, E, BETA, gz)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return rows / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = CPU_SAMPLE_ROWS
+    rate, dt, threads = cpu_reference_rate(torch, args.steps, args.warmup, rows)
+    sample = (f"{rows} latents x D={D} against the full K={K} codebook per step (the reference's dense N x K fp32 "
+              f"temporaries are {rows * K * 4 / 2**30:.2f} GiB each; cost is linear in N)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"VQ fwd+bwd, K={K}, D={D}, CPU port of models/shelgon3/VectorQuantizer.py on a "
+                               f"{rows}-latent sample per step", "K": K, "D": D, "latents_per_step": rows},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_kvq(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- kvq has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import kindergarten_vq_vae_b200 as kvq
+    from kindergarten_vq_vae_b200 import _lib
+    F = kvq.functional
+    lib = _lib.load()
+
+    n_rows = N_PER_GPU
+    z, gz, E = synth_device(torch, dev, n_rows, SEED + 1 + rank)
+    z3 = z.view(n_rows // 64, 64, D).requires_grad_(True)     # (B=16384, S=64, D): the module's (B,S,D) input
+    gz3 = gz.view_as(z3)
+    one = torch.ones((), device=dev)
+    if world > 1:
+        vq = kvq.BatchShardedVectorQuantizer(K, D, BETA, vq_codebook_init_values=E, search="tf32").to(dev)
+    else:
+        vq = kvq.VectorQuantizer(K, D, BETA, vq_codebook_init_values=E, search="tf32", min_encodings=False).to(dev)
+
+    def step():
+        z3.grad = None
+        vq.embedding.weight.grad = None
+        loss, z_q, perp, _, idx = vq.forward(z3, dev)
+        torch.autograd.backward([loss, z_q], [one, gz3])
+        return loss, perp
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream, max over ranks -------------
+    lib.kvq_profile_enable(1)
+    launches0 = lib.kvq_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, perp = step()
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    total_ms = e0.elapsed_time(e1)
+    launches = lib.kvq_launch_count() - launches0
+    lib.kvq_profile_enable(0)
+    ms = (ctypes.c_double * 6)()
+    cnt = (ctypes.c_int * 6)()
+    _lib.check(lib.kvq_profile_collect(ms, cnt, 6), "kvq_profile_collect")
+    prof = {tag: (ms[i] / cnt[i] if cnt[i] else None) for i, tag in enumerate(_lib.PROF_TAGS)}
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = n_rows * world / (ms_per_step * 1e-3)
+
+    # ---- end to end with host buffers (H2D + compute + D2H inside the timed region) --------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(torch, dist, F, vq, z, gz, E, dev, world, args)
+
+    # ---- rooflines -----------------------------------------------------------------------------------------
+    pk = peaks()
+    sustained = args.steps * ms_per_step > 1000.0
+    tf32_peak = (pk["bf16_tflops_sustained"] if sustained else pk["bf16_tflops"]) / 2.0
+    roof = None
+    if prof["search"]:
+        flops = 2.0 * n_rows * K * D
+        ach = flops / (prof["search"] * 1e-3) / 1e12
+        roof = {"kernel": "search_tf32_kernel (tcgen05 distance+argmin)", "bound": "tensor", "achieved": ach,
+                "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+                "peak_source": f"{pk['source']} bf16 dense {'sustained' if sustained else 'burst'} / 2 "
+                               "(tf32 runs at half the bf16 rate; tf32 itself is not in MEASURED_PEAKS.json)",
+                "algorithmic_flops_per_launch": flops, "ms_per_launch": prof["search"]}
+    others = {}
+    if prof["quantize"]:
+        b = 3 * 4.0 * n_rows * D + 8.0 * n_rows + 4.0 * K
+        others["quantize"] = {"bound": "hbm", "achieved": b / (prof["quantize"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                              "unit": "GB/s", "frac": b / (prof["quantize"] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                              "algorithmic_bytes_per_launch": b, "ms_per_launch": prof["quantize"]}
+    if prof["bwd_segmented"]:
+        b = 3 * 4.0 * n_rows * D + 8.0 * n_rows + 4.0 * K * D
+        others["bwd_segmented"] = {"bound": "hbm", "achieved": b / (prof["bwd_segmented"] * 1e-3) / 1e9,
+                                   "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                   "frac": b / (prof["bwd_segmented"] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                   "algorithmic_bytes_per_launch": b, "ms_per_launch": prof["bwd_segmented"]}
+
+    # ---- CPU baseline beside it (rank 0, single-GPU run only) ---------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, dt, threads = cpu_reference_rate(torch, 2, 1, CPU_SAMPLE_ROWS)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{CPU_SAMPLE_ROWS} latents x D={D} vs K={K}, literal port of the reference step "
+                         f"(oracle.vq_oracle.literal_step_cpu), 1 warm-up + 2 timed iterations, {dt:.2f} s each"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32 (fp32 accumulate; fp32 everywhere outside the distance GEMM)",
+            "data": "synthetic",
+            "config": {"workload": f"VQ fwd+bwd, N={n_rows} latents per GPU, D={D}, K={K}, beta={BETA}",
+                       "latents_per_gpu": n_rows, "D": D, "K": K,
+                       "parallelism": "single GPU" if world == 1 else f"batch-sharded x{world}, codebook replicated, "
+                                      "all-reduce of dE + histogram + loss partial (NCCL)",
+                       "l2": "inputs exceed L2 (z and g_zq are 1 GiB each per step; L2 is 126 MB), no flush needed",
+                       "codebook_init": "data-scale: N(0,1) rows + 0.1 noise"},
+            "roofline": roof, "roofline_other_kernels": others, "kernel_ms": prof,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "loss": float(loss), "perplexity": float(perp),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_e2e(torch, dist, F, vq, z, gz, E, dev, world, args):
+    """Same metric through the public host-buffer call: every step copies z and g_zq (and the codebook) from
+    pinned host memory, runs forward + backward, and copies z_q, idx, dz, dE, loss, perplexity back."""
+    n_rows = z.shape[0]
+    steps = max(2, min(args.steps, 5))
+    zh = torch.empty(n_rows, D, pin_memory=True).copy_(z)
+    gh = torch.empty(n_rows, D, pin_memory=True).copy_(gz)
+    Eh = torch.empty(K, D, pin_memory=True).copy_(E)
+    h2d = (2 * n_rows * D + K * D) * 4 + 4
+    d2h = (2 * n_rows * D + K * D) * 4 + 8 * n_rows + 8
+    torch.cuda.synchronize()
+    if world == 1:
+        out = None
+        for _ in range(2):
+            out = F.forward_backward_host(zh, Eh, gh, 1.0, BETA, mode="tf32", rows_per_chunk=args.chunk_rows, out=out)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = F.forward_backward_host(zh, Eh, gh, 1.0, BETA, mode="tf32", rows_per_chunk=args.chunk_rows, out=out)
+        dt = (time.perf_counter() - t0) / steps
+        api = "kvq_forward_backward_host (C ABI, pinned host buffers, chunked copy/compute overlap)"
+        F._lib.load().kvq_host_release()
+    else:
+        one = torch.ones((), device=dev)
+        outs = dict(z_q=torch.empty(n_rows, D, pin_memory=True), dz=torch.empty(n_rows, D, pin_memory=True),
+                    idx=torch.empty(n_rows, dtype=torch.int64, pin_memory=True), dE=torch.empty(K, D, pin_memory=True),
+                    scal=torch.empty(2, pin_memory=True))
+
+        def host_step():
+            zd = zh.to(dev, non_blocking=True).view(n_rows // 64, 64, D).requires_grad_(True)
+            gd = gh.to(dev, non_blocking=True).view(n_rows // 64, 64, D)
+            vq.embedding.weight.data.copy_(Eh, non_blocking=True)
+            vq.embedding.weight.grad = None
+            loss, z_q, perp, _, idx = vq.forward(zd, dev)
+            torch.autograd.backward([loss, z_q], [one, gd])
+            outs["z_q"].copy_(z_q.detach().view(n_rows, D), non_blocking=True)
+            outs["dz"].copy_(zd.grad.view(n_rows, D), non_blocking=True)
+            outs["idx"].copy_(idx.view(-1), non_blocking=True)
+            outs["dE"].copy_(vq.embedding.weight.grad, non_blocking=True)
+            outs["scal"][0:1].copy_(loss.detach().view(1), non_blocking=True)
+            outs["scal"][1:2].copy_(perp.view(1), non_blocking=True)
+            torch.cuda.synchronize()
+
+        host_step()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            host_step()
+        dist.barrier()
+        dt = (time.perf_counter() - t0) / steps
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        api = "BatchShardedVectorQuantizer.forward/backward with pinned-host inputs and outputs (per rank)"
+    return {"value": n_rows * world / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": dt * 1e3, "steps": steps, "api": api}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kvq", choices=["kvq", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--chunk-rows", type=int, default=131072)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "kvq":
+        args.warmup = 3          # timing rule: at least three warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_kvq(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,24 @@ enum {
 int kvq_version(void);
 const char* kvq_last_error(void);
 
+/* Number of CUDA kernels the library has launched so far in this process (all entry points, all threads). */
+long long kvq_launch_count(void);
+
+/* Optional per-kernel timing: while enabled, the library brackets its main kernels with CUDA events on the
+ * launching stream.  kvq_profile_collect synchronises those events, returns the summed milliseconds and launch
+ * counts per tag, and clears the record.  Used by bench.py for the roofline of each kernel. */
+enum {
+  KVQ_PROF_NORMS = 0,          /* code_norms_kernel */
+  KVQ_PROF_SEARCH = 1,         /* distance + argmin kernel (tf32 tcgen05 or fp32) */
+  KVQ_PROF_QUANTIZE = 2,       /* gather + straight-through + loss partial + histogram */
+  KVQ_PROF_FINALIZE = 3,       /* loss / perplexity */
+  KVQ_PROF_BWD_BUCKET = 4,     /* dE memset + histogram scan + counting-sort fill */
+  KVQ_PROF_BWD_SEGMENTED = 5,  /* dz + segmented scatter-add -> dE */
+  KVQ_PROF_NTAGS = 6
+};
+int kvq_profile_enable(int on);
+int kvq_profile_collect(double* ms_per_tag, int* launches_per_tag, int ntags);
+
 /* Device facts the host side needs for grid sizing / reporting. */
 int kvq_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

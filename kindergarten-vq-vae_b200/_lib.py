@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libkvq.so")
 
 KVQ_OK = 0
 SEARCH_AUTO, SEARCH_TF32, SEARCH_FP32 = 0, 1, 2
+PROF_TAGS = ["norms", "search", "quantize", "finalize", "bwd_bucket", "bwd_segmented"]
 SEARCH_MODES = {"auto": SEARCH_AUTO, "tf32": SEARCH_TF32, "fp32": SEARCH_FP32}
 
 _P = c_void_p
@@ -22,6 +23,9 @@ _P = c_void_p
 SIGNATURES = {
     "kvq_version": (c_int, []),
     "kvq_last_error": (c_char_p, []),
+    "kvq_launch_count": (ctypes.c_longlong, []),
+    "kvq_profile_enable": (c_int, [c_int]),
+    "kvq_profile_collect": (c_int, [_P, _P, c_int]),
     "kvq_device_info": (c_int, [_P, _P, _P]),
     "kvq_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64]),
     "kvq_code_norms": (c_int, [_P, c_int64, c_int, _P, c_int64, _P]),

@@ -2,6 +2,10 @@
 // forward / backward orchestration live here; kernels live in the other translation units.
 #include <stdarg.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "kvq_common.cuh"
 
 namespace kvq {
@@ -18,6 +22,26 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
   return KVQ_ERR_CUDA;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static std::atomic<int> g_prof_on{0};
+struct ProfRec { int tag; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(int tag, cudaStream_t st) : tag_(tag), st_(st) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) { e0_ = e1_ = nullptr; return; }
+  cudaEventRecord(e0_, st_);
+}
+ProfScope::~ProfScope() {
+  if (!e0_) return;
+  cudaEventRecord(e1_, st_);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof.push_back({tag_, e0_, e1_});
 }
 
 struct DevInfo { int sms = 0, major = 0, minor = 0; bool ok = false; };
@@ -86,6 +110,33 @@ using namespace kvq;
 extern "C" {
 
 int kvq_version(void) { return 100; }
+
+long long kvq_launch_count(void) { return g_launches.load(); }
+
+int kvq_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return KVQ_OK;
+}
+
+int kvq_profile_collect(double* ms_per_tag, int* launches_per_tag, int ntags) {
+  KVQ_REQUIRE(ms_per_tag && launches_per_tag && ntags >= KVQ_PROF_NTAGS, KVQ_ERR_ARG, "kvq_profile_collect: bad arguments");
+  for (int i = 0; i < ntags; ++i) { ms_per_tag[i] = 0.0; launches_per_tag[i] = 0; }
+  std::vector<ProfRec> recs;
+  {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    recs.swap(g_prof);
+  }
+  int status = KVQ_OK;
+  for (const ProfRec& r : recs) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (e != cudaSuccess) status = cuda_fail(e, "profile event", __FILE__, __LINE__);
+    else if (r.tag >= 0 && r.tag < ntags) { ms_per_tag[r.tag] += ms; launches_per_tag[r.tag] += 1; }
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  return status;
+}
 const char* kvq_last_error(void) { return g_err; }
 
 int kvq_device_info(int* sms, int* major, int* minor) {
@@ -167,13 +218,16 @@ int kvq_forward(const float* z, const float* E, int64_t N, int D, int64_t K, flo
   KVQ_REQUIRE(ws_bytes >= w.bytes, KVQ_ERR_WORKSPACE, "kvq_forward: workspace %zu < %zu bytes", ws_bytes, w.bytes);
   int m; rc = resolve_mode(mode, N, D, K, &m); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); if (rc) return rc;
+  { ProfScope ps(KVQ_PROF_NORMS, st); rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); }
+  if (rc) return rc;
   if (m == KVQ_SEARCH_TF32) rc = launch_search_tf32(z, E, w.e2, N, D, K, 0, idx, w.keys, 0, st);
   else rc = launch_search_fp32(z, E, w.e2, N, D, K, 0, idx, w.keys, 0, st);
   if (rc) return rc;
   KVQ_CUDA(cudaMemsetAsync(w.sq_sum, 0, sizeof(double), st));
   KVQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int32_t), st));
-  rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, w.sq_sum, hist, st); if (rc) return rc;
+  { ProfScope ps(KVQ_PROF_QUANTIZE, st); rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, w.sq_sum, hist, st); }
+  if (rc) return rc;
+  ProfScope ps(KVQ_PROF_FINALIZE, st);
   return launch_finalize(w.sq_sum, hist, N, D, K, beta, loss, perplexity, st);
 }
 

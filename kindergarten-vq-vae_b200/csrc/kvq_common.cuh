@@ -20,7 +20,21 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (_e != cudaSuccess) return ::kvq::cuda_fail(_e, #call, __FILE__, __LINE__);   \
   } while (0)
 
-#define KVQ_LAUNCH_CHECK() KVQ_CUDA(cudaGetLastError())
+void count_launch();  // every kernel launch of the library is counted (kvq_launch_count)
+#define KVQ_LAUNCH_CHECK()            \
+  do {                                \
+    ::kvq::count_launch();            \
+    KVQ_CUDA(cudaGetLastError());     \
+  } while (0)
+
+// Optional per-kernel timing with CUDA events on the launching stream (kvq_profile_enable / kvq_profile_collect).
+struct ProfScope {
+  ProfScope(int tag, cudaStream_t st);
+  ~ProfScope();
+  int tag_;
+  cudaStream_t st_;
+  cudaEvent_t e0_ = nullptr, e1_ = nullptr;
+};
 
 #define KVQ_REQUIRE(cond, code, ...)        \
   do {                                      \

@@ -129,8 +129,11 @@ int launch_search_fp32(const float* z, const float* E, const float* e2, int64_t 
     if (rc) return rc;
   }
   dim3 grid((unsigned)m_tiles, (unsigned)split);
-  search_fp32_kernel<<<grid, F_THREADS, 0, st>>>(z, E, e2, N, D, K, k_offset, tiles_per_split, idx, keys, use_atomic);
-  KVQ_LAUNCH_CHECK();
+  {
+    ProfScope ps(KVQ_PROF_SEARCH, st);
+    search_fp32_kernel<<<grid, F_THREADS, 0, st>>>(z, E, e2, N, D, K, k_offset, tiles_per_split, idx, keys, use_atomic);
+    KVQ_LAUNCH_CHECK();
+  }
   if (use_atomic && idx) return launch_keys_to_idx(keys, N, idx, st);
   return KVQ_OK;
 }

@@ -433,8 +433,11 @@ int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t 
   }
   KVQ_CUDA(cudaFuncSetAttribute(search_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)min_i64(p.n_items, sms);
-  search_tf32_kernel<<<grid, NUM_THREADS, smem, st>>>(mz, me, p);
-  KVQ_LAUNCH_CHECK();
+  {
+    ProfScope ps(KVQ_PROF_SEARCH, st);
+    search_tf32_kernel<<<grid, NUM_THREADS, smem, st>>>(mz, me, p);
+    KVQ_LAUNCH_CHECK();
+  }
   if (p.use_atomic && idx && !keys_accumulate) return launch_keys_to_idx(keys, N, idx, st);
   return KVQ_OK;
 }

@@ -242,3 +242,28 @@ def dp_merge(parts, beta: float, N_global: int, D: int, K: int):
     m = np.float32(sq / (N_global * D))
     loss = np.float32(m + np.float32(beta) * m)
     return torch.tensor(loss), perplexity_from_counts(counts, N_global)
+
+
+# ---- literal CPU port of the reference step (the `cpu_baseline` / `--impl reference` arm of bench.py) -------
+
+def literal_step_cpu(z: torch.Tensor, E: torch.Tensor, beta: float, g_zq: torch.Tensor):
+    """One forward + backward exactly as the reference executes it, dense N x K temporaries included
+    (VectorQuantizer.py:55-85 followed by autograd): distance matrix, argmin, host-built one-hot, one-hot GEMM
+    lookup, two mean-squared terms, straight-through, perplexity; backward with g_zq upstream and unit weight on
+    the loss.  This is what the reference costs on CPU -- `forward_fp32` above is a lighter restatement used for
+    checking, this one is used for timing.  Returns (loss, perplexity, idx, dz, dE)."""
+    K, D = E.shape
+    zr = z.detach().clone().requires_grad_(True)
+    W = E.detach().clone().requires_grad_(True)
+    flat = zr.view(-1, D)
+    d = torch.sum(flat ** 2, dim=1, keepdim=True) + torch.sum(W ** 2, dim=1) - 2 * torch.matmul(flat, W.t())
+    nearest = torch.argmin(d, dim=1).unsqueeze(1)
+    hot = torch.zeros(nearest.shape[0], K)
+    hot.scatter_(1, nearest, 1)
+    q = torch.matmul(hot, W).view(zr.shape)
+    loss = torch.mean((q.detach() - zr) ** 2) + beta * torch.mean((q - zr.detach()) ** 2)
+    out = zr + (q - zr).detach()
+    usage = torch.mean(hot, dim=0)
+    perplexity = torch.exp(-torch.sum(usage * torch.log(usage + 1e-10)))
+    torch.autograd.backward([loss, out], [torch.ones(()), g_zq])
+    return loss.detach(), perplexity.detach(), nearest.view(*z.shape[:-1], 1), zr.grad, W.grad

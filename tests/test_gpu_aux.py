@@ -1,0 +1,89 @@
+"""GPU tests of the helpers named by north_star (common/metrics.py, common/tensor_utils.py), the dense one-hot and
+the host-buffer end-to-end entry point."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden
+from oracle import vq_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _kvq():
+    import kindergarten_vq_vae_b200 as k
+    return k
+
+
+def test_seq_acc_golden_and_random():
+    k = _kvq()
+    d = np.load(os.path.join(GOLDEN, "seq_acc.npz"))
+    acc, per = k.seq_acc(torch.from_numpy(d["a"]).to(DEV), torch.from_numpy(d["b"]).to(DEV))
+    assert float(acc) == float(d["acc"]) and np.array_equal(per.cpu().numpy(), d["per"])
+    a = torch.randint(0, 3, (513, 12)); b = torch.randint(0, 3, (513, 12))
+    acc, per = k.seq_acc(a.to(DEV), b.to(DEV))
+    ra, rp = O.seq_acc(a, b)
+    assert float(acc) == float(ra) and torch.equal(per.cpu(), rp)
+    with pytest.raises(AssertionError):
+        k.seq_acc(a.float().to(DEV), b.to(DEV))
+    with pytest.raises(AssertionError):
+        k.seq_acc(a[:5].to(DEV), b.to(DEV))
+
+
+def test_replace_pct_rand_values_counts_and_range():
+    k = _kvq()
+    t = torch.full((512, 12), -7, dtype=torch.int64, device=DEV)     # sentinel outside [low, high)
+    for pct in (0.1, 0.15, 0.69, 1.0):
+        out = k.replace_pct_rand_values(t, pct, 0, 30522, seed=5)
+        changed = out != -7
+        assert int(changed.sum()) == int(t.numel() * pct)             # exactly int(numel*pct), tensor_utils.py:29
+        assert int(out[changed].min()) >= 0 and int(out[changed].max()) < 30522
+        assert torch.equal(out, k.replace_pct_rand_values(t, pct, 0, 30522, seed=5))       # reproducible per seed
+        assert not torch.equal(out, k.replace_pct_rand_values(t, pct, 0, 30522, seed=6))
+    # positions are spread over the tensor, not clustered at the front
+    out = k.replace_pct_rand_values(t, 0.5, 0, 10, seed=1)
+    first, second = (out[:256] != -7).float().mean(), (out[256:] != -7).float().mean()
+    assert abs(float(first) - 0.5) < 0.05 and abs(float(second) - 0.5) < 0.05
+
+
+def test_change_percentage_of_elements_slices():
+    k = _kvq()
+    t = torch.full((20, 8), -1, dtype=torch.int64, device=DEV)
+    out = k.change_percentage_of_elements(t, 1, 0.6, 5, 9, seed=3)
+    cols = (out != -1).all(0)
+    assert int(cols.sum()) == int(8 * 0.6) and bool(((out != -1).any(0) == cols).all())   # whole columns
+    assert bool((out[:, cols] == out[0:1, cols]).all())                                  # one value per column
+    assert int(out[:, cols].min()) >= 5 and int(out[:, cols].max()) < 9
+    out0 = k.change_percentage_of_elements(t, 0, 0.25, 0, 100, seed=3)
+    rows = (out0 != -1).all(1)
+    assert int(rows.sum()) == 5 and bool((out0[rows] == out0[rows][:, :1]).all())
+    with pytest.raises(ValueError):
+        k.change_percentage_of_elements(t, 2, 0.5, 0, 3)
+
+
+def test_host_end_to_end_matches_device_path():
+    k = _kvq()
+    F = k.functional
+    gen = torch.Generator().manual_seed(11)
+    N, D, K = 3000, 256, 700
+    z = torch.randn(N, D, generator=gen).pin_memory()
+    E = torch.randn(K, D, generator=gen).pin_memory()
+    g = torch.randn(N, D, generator=gen).pin_memory()
+    out = F.forward_backward_host(z, E, g, 1.25, 0.25, mode="tf32", rows_per_chunk=1024)
+    zd, Ed, gd = z.to(DEV), E.to(DEV), g.to(DEV)
+    loss, z_q, perp, idx, hist = F.vq_forward(zd, Ed, 0.25, mode="tf32")
+    dz, dE = F.vq_backward(zd, Ed, idx, hist, 0.25, g_zq=gd, g_loss=torch.tensor(1.25, device=DEV))
+    par = O.index_parity(out["idx"], idx.cpu(), z, E)       # chunked search may split the code range differently
+    assert par.unexcused == 0
+    if par.raw_mismatch == 0:
+        assert torch.equal(out["z_q"], z_q.cpu())
+        assert abs(float(out["loss"]) - float(loss)) <= 1e-6 * float(loss)
+        assert abs(float(out["perplexity"]) - float(perp)) <= 1e-6 * float(perp)
+        assert torch.allclose(out["dz"], dz.cpu(), rtol=1e-6, atol=1e-8)
+        assert (out["dE"] - dE.cpu()).abs().max() <= 1e-5 * dE.abs().max()
+    ref = O.forward_fp32(z, E, 0.25)
+    assert O.index_parity(out["idx"], ref.idx, z, E).unexcused == 0
+    F._lib.load().kvq_host_release()
