@@ -1,21 +1,36 @@
 // Tensor-core distance + argmin for sm_100a: TMA -> shared memory -> tcgen05.mma.kind::tf32 -> TMEM -> fused
 // argmin epilogue.  Replaces models/shelgon3/VectorQuantizer.py:59-65; the N x K distance matrix lives only in
-// TMEM, 128 x 256 fp32 at a time, and never reaches shared or global memory.
+// TMEM, 128 x 256 fp32 per SM at a time, and never reaches shared or global memory.
 //
 //   score(i,k) = |E_k|^2 - 2 z_i . E_k          (tf32 products, fp32 accumulate; |z_i|^2 is row-constant)
 //   idx[i]     = argmin_k score(i,k), ties -> lowest k
 //
-// Work decomposition.  An "item" is one tile of 128 latents swept over a range of 256-code tiles; a persistent
-// CTA (one per SM) takes items round-robin.  For D <= 256 the latent tile (128 x D fp32, <= 128 KB) is loaded
-// once per item and stays resident in shared memory while codebook tiles stream through a ring of 32 KB stages,
-// so the only steady-state operand traffic is the codebook (L2 resident).  For larger D both operands stream.
+// Work decomposition.  An "item" is a tile of 128*CG latents swept over a range of 256-code tiles; persistent
+// CTAs (one per SM) take items round-robin.  CG is the tcgen05 cta_group:
+//   CG = 2 (default): the two CTAs of a cluster form one MMA of M = 256: each CTA keeps its own 128-latent tile
+//           and loads HALF of every codebook tile (128 codes x 32 floats = 16 KB per stage); the tensor cores
+//           read both halves.  Per SM that halves the codebook bytes pulled from L2 and doubles the number of
+//           pipeline stages that fit beside the resident latent tile (6 instead of 3), which is what hides the
+//           ~1 us TMA round trip (measured: 1-CTA form was 66 % tensor-pipe active, limited by 3 stages).
+//   CG = 1: single-CTA form (kept for A/B measurements: KVQ_TF32_CTA_GROUP=1).
+// For D <= 256 the latent tile (128 x D fp32, <= 128 KB) is loaded once per item and stays resident in shared
+// memory while codebook tiles stream through the stage ring; for larger D both operands stream.
 //
-// Warp roles (320 threads):  warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..9 = epilogue.  The accumulator is double buffered in TMEM (2 x 256 columns = all 512), so the argmin
-// epilogue of code tile j overlaps the MMAs of tile j+1.  Epilogue warp w reads TMEM lanes 32*(w%4).. (its
-// hardware lane quarter) and one half of the 256 columns; each thread owns one latent row and keeps four
-// independent running (min, index) chains.
+// Warp roles (320 threads):  warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane of
+// the leader CTA), warps 2..9 = epilogue.  The accumulator is double buffered in TMEM (2 x 256 columns = all
+// 512), so the argmin epilogue of code tile j overlaps the MMAs of tile j+1.  Epilogue warp w reads TMEM lanes
+// 32*(w%4).. (its hardware lane quarter) and one half of the 256 columns; each thread owns one latent row and
+// keeps four independent running (min, index) chains.
+//
+// Barrier protocol (mbarriers in shared memory, same offsets in both CTAs of a pair):
+//   full[s]      leader only   1 arrival (leader producer, expect_tx of BOTH CTAs' bytes) + TMA complete_tx
+//   empty[s]     every CTA     tcgen05.commit (multicast to the pair) when the MMAs that read stage s retire
+//   a_full       leader only   resident latent tiles of both CTAs have landed
+//   a_empty      every CTA     tcgen05.commit after the last MMA of the item
+//   tm_full[a]   every CTA     tcgen05.commit when accumulator a is complete
+//   tm_empty[a]  leader only   8*CG arrivals: every epilogue warp of the pair has drained accumulator a
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime, no -lcuda needed)
+#include <stdlib.h>
 
 #include "kvq_common.cuh"
 
@@ -23,23 +38,23 @@ namespace kvq {
 
 namespace t5 {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_N = 256;
+constexpr int BLOCK_M = 128;                        // latents per CTA
+constexpr int BLOCK_N = 256;                        // codes per MMA (per pair when CG = 2)
 constexpr int BLOCK_K = 32;                         // fp32 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 8;                           // tf32
 constexpr int A_KBLOCK_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 4;   // 32 KB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;   // 320
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
 constexpr int SMEM_LIMIT = 232448;                  // 227 KB opt-in maximum per CTA
 constexpr int SMEM_CTRL_BYTES = 1024 + 1024;        // barriers + tmem slot | cross-half merge scratch
 constexpr int RESIDENT_MAX_D = 256;
 
 // tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor bit layout): c_format F32 @4, a/b_format TF32 @7/@10,
 // a/b K-major (bits 15/16 = 0), n_dim = N>>3 @17, m_dim = M>>4 @24.
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                           ((uint32_t)(BLOCK_M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 struct Params {
   int64_t N, K, k_offset;
@@ -48,8 +63,7 @@ struct Params {
   int n_tiles;          // ceil(K / 256)
   int tiles_per_split;  // code tiles per item
   int ksplit;
-  int64_t m_tiles;
-  int64_t n_items;      // m_tiles * ksplit
+  int64_t n_items;      // ceil(m_tiles / CG) * ksplit
   int resident;         // latent tile resident in smem
   int stages;
   int use_atomic;       // MIN-combine into keys (split code range or caller-accumulated keys)
@@ -61,6 +75,21 @@ struct Params {
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -69,6 +98,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on a barrier that may live in the peer CTA (address from map_to_cta)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -92,22 +125,48 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+  } else {  // data lands in this CTA, completion bytes are signalled on the LEADER CTA's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+  }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// arrive on `bar` (same offset in every CTA of the pair) once all previously issued MMAs have retired
+template <int CG>
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+  constexpr uint32_t idesc = make_idesc(BLOCK_M * CG, BLOCK_N);
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
 }
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
@@ -133,9 +192,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------
+template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
                    const Params p) {
+  constexpr int B_ROWS = BLOCK_N / CG;                 // codebook rows this CTA loads per stage
+  constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 4;  // 32 KB (CG=1) / 16 KB (CG=2)
+
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms (8 rows x 128 B).
   const uint32_t raw = smem_u32(smem_raw);
@@ -144,9 +207,12 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+  const int64_t first_item = (int64_t)(blockIdx.x / CG);
+  const int64_t item_stride = (int64_t)(gridDim.x / CG);
 
   // shared-memory map: [control 2 KB][resident latent tile (resident mode)][stage ring]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar_full = base;                      // [MAX_STAGES]
   const uint32_t bar_empty = base + 8 * MAX_STAGES;    // [MAX_STAGES]
   const uint32_t bar_a_full = base + 16 * MAX_STAGES;
@@ -156,7 +222,6 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 16 * MAX_STAGES + 48);
   float* merge_val = reinterpret_cast<float*>(smem + 1024);
   uint32_t* merge_idx = reinterpret_cast<uint32_t*>(smem + 1024 + 512);
-  (void)bars;
 
   const uint32_t a_bytes = p.resident ? (uint32_t)p.num_kblocks * A_KBLOCK_BYTES : 0u;
   const uint32_t a_region = base + SMEM_CTRL_BYTES;
@@ -172,52 +237,62 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
     mbar_init(bar_a_empty, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tm_full + 8 * a, 1);
-      mbar_init(bar_tm_empty + 8 * a, NUM_EPI_WARPS);
+      mbar_init(bar_tm_empty + 8 * a, NUM_EPI_WARPS * CG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // one warp allocates all 512 TMEM columns (two 128 x 256 fp32 accumulators)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {  // one warp (per CTA) allocates all 512 TMEM columns: two 128 x 256 fp32 accumulators
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_z) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_e) : "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs are initialised
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer (every CTA) ===========================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, a_phase = 0;
-      for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int64_t m_tile = item / p.ksplit;
+      // completion bytes of both CTAs are counted on the leader's barriers
+      const uint32_t a_full_sig = (CG == 2) ? map_to_cta(bar_a_full, 0) : bar_a_full;
+      for (int64_t item = first_item; item < p.n_items; item += item_stride) {
+        const int64_t m_group = item / p.ksplit;
         const int ks = (int)(item % p.ksplit);
-        const int m0 = (int)(m_tile * BLOCK_M);
+        const int m0 = (int)((m_group * CG + cta_rank) * BLOCK_M);
         const int t_begin = ks * p.tiles_per_split;
         const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
         if (p.resident) {
           mbar_wait(bar_a_empty, a_phase ^ 1);          // previous item's MMAs have finished reading the tile
-          mbar_expect_tx(bar_a_full, a_bytes);
+          if (leader) mbar_expect_tx(bar_a_full, a_bytes * CG);
           for (int kb = 0; kb < p.num_kblocks; ++kb)
-            tma_load_2d(a_region + kb * A_KBLOCK_BYTES, &tmap_z, kb * BLOCK_K, m0, bar_a_full);
+            tma_load_2d<CG>(a_region + kb * A_KBLOCK_BYTES, &tmap_z, kb * BLOCK_K, m0, a_full_sig);
           a_phase ^= 1;
         }
         for (int t = t_begin; t < t_end; ++t) {
-          const int n0 = t * BLOCK_N;
+          const int n0 = t * BLOCK_N + (int)cta_rank * B_ROWS;
           for (int kb = 0; kb < p.num_kblocks; ++kb) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             const uint32_t sbase = ring + stage * stage_bytes;
-            mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
+            const uint32_t full_own = bar_full + 8 * stage;
+            const uint32_t full_sig = (CG == 2) ? map_to_cta(full_own, 0) : full_own;
+            if (leader) mbar_expect_tx(full_own, stage_bytes * CG);
             if (!p.resident) {
-              tma_load_2d(sbase, &tmap_z, kb * BLOCK_K, m0, bar_full + 8 * stage);
-              tma_load_2d(sbase + A_KBLOCK_BYTES, &tmap_e, kb * BLOCK_K, n0, bar_full + 8 * stage);
+              tma_load_2d<CG>(sbase, &tmap_z, kb * BLOCK_K, m0, full_sig);
+              tma_load_2d<CG>(sbase + A_KBLOCK_BYTES, &tmap_e, kb * BLOCK_K, n0, full_sig);
             } else {
-              tma_load_2d(sbase, &tmap_e, kb * BLOCK_K, n0, bar_full + 8 * stage);
+              tma_load_2d<CG>(sbase, &tmap_e, kb * BLOCK_K, n0, full_sig);
             }
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
@@ -225,10 +300,10 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (leader CTA, one lane) ===========================
+    if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
-      for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int64_t item = first_item; item < p.n_items; item += item_stride) {
         const int ks = (int)(item % p.ksplit);
         const int t_begin = ks * p.tiles_per_split;
         const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
@@ -238,7 +313,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
           tc_fence_after();
         }
         for (int t = t_begin; t < t_end; ++t) {
-          mbar_wait(bar_tm_empty + 8 * acc, acc_phase ^ 1);   // epilogue has drained this accumulator
+          mbar_wait(bar_tm_empty + 8 * acc, acc_phase ^ 1);   // every epilogue warp has drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
           for (int kb = 0; kb < p.num_kblocks; ++kb) {
@@ -252,28 +327,28 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-              tc_mma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+              tc_mma_tf32<CG>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
             }
-            tc_commit(bar_empty + 8 * stage);                 // stage reusable once these MMAs retire
+            tc_commit<CG>(bar_empty + 8 * stage);             // stage reusable once these MMAs retire
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
-          tc_commit(bar_tm_full + 8 * acc);                   // accumulator complete -> epilogue
+          tc_commit<CG>(bar_tm_full + 8 * acc);               // accumulator complete -> epilogues of the pair
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
-        if (p.resident) tc_commit(bar_a_empty);               // latent tile may be overwritten
+        if (p.resident) tc_commit<CG>(bar_a_empty);           // latent tiles may be overwritten
       }
     }
     __syncwarp();
   } else {
-    // =========================== argmin epilogue ===========================
+    // =========================== argmin epilogue (every CTA) ===========================
     const int ew = warp - 2;
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int half = ew >> 2;            // which 128 of the 256 accumulator columns
     const int row_in_tile = quarter * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
-    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int64_t m_tile = item / p.ksplit;
+    for (int64_t item = first_item; item < p.n_items; item += item_stride) {
+      const int64_t m_group = item / p.ksplit;
       const int ks = (int)(item % p.ksplit);
       const int t_begin = ks * p.tiles_per_split;
       const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
@@ -305,7 +380,10 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tm_empty + 8 * acc);
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(map_to_cta(bar_tm_empty + 8 * acc, 0));
+          else mbar_arrive(bar_tm_empty + 8 * acc);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -322,7 +400,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
         const float ov = merge_val[row_in_tile];
         const uint32_t oi = merge_idx[row_in_tile];
         if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        const int64_t row = m_tile * BLOCK_M + row_in_tile;
+        const int64_t row = (m_group * CG + cta_rank) * BLOCK_M + row_in_tile;
         if (row < p.N) {
           const uint32_t gi = (uint32_t)(bi + p.k_offset);
           const long long key = pack_key(bv, gi);
@@ -339,10 +417,13 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody touches the peer's smem / TMEM after this
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if constexpr (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -364,6 +445,9 @@ static EncodeTiledFn get_encoder() {
 }
 
 // 2-D row-major fp32 matrix (rows x D), box = box_rows x 32 floats, 128-byte swizzle, OOB rows read as zero.
+// With `round_tf32` the TMA unit rounds fp32 to tf32 (round-to-nearest) on the way into shared memory instead of
+// letting the tensor core truncate the low 13 mantissa bits: half the operand error, measurably fewer near-tie
+// index flips, and (fewer toggling bits) slightly lower power.
 static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int D, int box_rows, bool round_tf32) {
   EncodeTiledFn enc = get_encoder();
   KVQ_REQUIRE(enc, KVQ_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
@@ -379,6 +463,75 @@ static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int D, int b
   return KVQ_OK;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
+template <int CG>
+static int launch_cg(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t k_offset,
+                     int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st) {
+  constexpr int B_STAGE_BYTES = (BLOCK_N / CG) * BLOCK_K * 4;
+  Params p;
+  p.N = N; p.K = K; p.k_offset = k_offset; p.D = D;
+  p.num_kblocks = D / BLOCK_K;
+  p.n_tiles = (int)((K + BLOCK_N - 1) / BLOCK_N);
+  const int64_t m_tiles = (N + BLOCK_M - 1) / BLOCK_M;
+  const int64_t m_groups = (m_tiles + CG - 1) / CG;
+  const int groups = sm_count() / CG;                      // concurrently resident CTA groups
+  int ksplit = 1;
+  if (m_groups < groups) ksplit = (int)min_i64(p.n_tiles, (groups + m_groups - 1) / m_groups);
+  p.tiles_per_split = (p.n_tiles + ksplit - 1) / ksplit;
+  p.ksplit = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.n_items = m_groups * p.ksplit;
+  p.resident = (D <= RESIDENT_MAX_D) ? 1 : 0;
+  const int a_bytes = p.resident ? p.num_kblocks * A_KBLOCK_BYTES : 0;
+  const int stage_bytes = p.resident ? B_STAGE_BYTES : (A_KBLOCK_BYTES + B_STAGE_BYTES);
+  int stages = (SMEM_LIMIT - 1024 - SMEM_CTRL_BYTES - a_bytes) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  const int cap = env_int("KVQ_TF32_MAX_STAGES", 0);
+  if (cap >= 2 && stages > cap) stages = cap;
+  KVQ_REQUIRE(stages >= 2, KVQ_ERR_SHAPE, "tf32 search: no room for a 2-stage ring at D=%d", D);
+  p.stages = stages;
+  p.use_atomic = (p.ksplit > 1 || keys_accumulate) ? 1 : 0;
+  p.e2 = e2; p.idx = idx; p.keys = keys;
+  KVQ_REQUIRE(!p.use_atomic || keys, KVQ_ERR_ARG, "kvq_search(tf32): split/accumulate search needs a keys buffer");
+  const size_t smem = 1024 + SMEM_CTRL_BYTES + (size_t)a_bytes + (size_t)stages * stage_bytes;
+
+  static const bool round_tf32 = env_int("KVQ_TMA_ROUND_TF32", 1) != 0;
+  CUtensorMap mz, me;
+  int rc = make_map(&mz, z, N, D, BLOCK_M, round_tf32);
+  if (rc) return rc;
+  rc = make_map(&me, E, K, D, BLOCK_N / CG, round_tf32);
+  if (rc) return rc;
+
+  if (p.use_atomic && !keys_accumulate) {
+    rc = launch_fill_keys(keys, N, st);
+    if (rc) return rc;
+  }
+  KVQ_CUDA(cudaFuncSetAttribute(search_tf32_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)(min_i64(p.n_items, groups) * CG);
+  {
+    ProfScope ps(KVQ_PROF_SEARCH, st);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    count_launch();
+    KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG>, mz, me, p));
+  }
+  if (p.use_atomic && idx && !keys_accumulate) return launch_keys_to_idx(keys, N, idx, st);
+  return KVQ_OK;
+}
+
 }  // namespace t5
 
 bool tf32_shape_ok(int64_t N, int D, int64_t K) {
@@ -387,59 +540,14 @@ bool tf32_shape_ok(int64_t N, int D, int64_t K) {
 
 int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
                        int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st) {
-  using namespace t5;
   if (N <= 0) return KVQ_OK;
   KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (got N=%lld D=%d K=%lld)",
               (long long)N, D, (long long)K);
   KVQ_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)E & 15) == 0, KVQ_ERR_ARG,
               "tf32 search needs 16-byte aligned z and E (TMA)");
-
-  Params p;
-  p.N = N; p.K = K; p.k_offset = k_offset; p.D = D;
-  p.num_kblocks = D / BLOCK_K;
-  p.n_tiles = (int)((K + BLOCK_N - 1) / BLOCK_N);
-  p.m_tiles = (N + BLOCK_M - 1) / BLOCK_M;
-  const int sms = sm_count();
-  int ksplit = 1;
-  if (p.m_tiles < sms) ksplit = (int)min_i64(p.n_tiles, (sms + p.m_tiles - 1) / p.m_tiles);
-  p.tiles_per_split = (p.n_tiles + ksplit - 1) / ksplit;
-  p.ksplit = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.n_items = p.m_tiles * p.ksplit;
-  p.resident = (D <= RESIDENT_MAX_D) ? 1 : 0;
-  const int a_bytes = p.resident ? p.num_kblocks * A_KBLOCK_BYTES : 0;
-  const int stage_bytes = p.resident ? B_STAGE_BYTES : (A_KBLOCK_BYTES + B_STAGE_BYTES);
-  int stages = (SMEM_LIMIT - 1024 - SMEM_CTRL_BYTES - a_bytes) / stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  KVQ_REQUIRE(stages >= 2, KVQ_ERR_SHAPE, "tf32 search: no room for a 2-stage ring at D=%d", D);
-  p.stages = stages;
-  p.use_atomic = (p.ksplit > 1 || keys_accumulate) ? 1 : 0;
-  p.e2 = e2; p.idx = idx; p.keys = keys;
-  KVQ_REQUIRE(!p.use_atomic || keys, KVQ_ERR_ARG, "kvq_search(tf32): split/accumulate search needs a keys buffer");
-  const size_t smem = 1024 + SMEM_CTRL_BYTES + (size_t)a_bytes + (size_t)stages * stage_bytes;
-
-  static const bool round_tf32 = []() {
-    const char* e = getenv("KVQ_TMA_ROUND_TF32");
-    return e && e[0] == '1';
-  }();
-  CUtensorMap mz, me;
-  int rc = make_map(&mz, z, N, D, BLOCK_M, round_tf32);
-  if (rc) return rc;
-  rc = make_map(&me, E, K, D, BLOCK_N, round_tf32);
-  if (rc) return rc;
-
-  if (p.use_atomic && !keys_accumulate) {
-    rc = launch_fill_keys(keys, N, st);
-    if (rc) return rc;
-  }
-  KVQ_CUDA(cudaFuncSetAttribute(search_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)min_i64(p.n_items, sms);
-  {
-    ProfScope ps(KVQ_PROF_SEARCH, st);
-    search_tf32_kernel<<<grid, NUM_THREADS, smem, st>>>(mz, me, p);
-    KVQ_LAUNCH_CHECK();
-  }
-  if (p.use_atomic && idx && !keys_accumulate) return launch_keys_to_idx(keys, N, idx, st);
-  return KVQ_OK;
+  static const int cta_group = t5::env_int("KVQ_TF32_CTA_GROUP", 2);
+  if (cta_group == 1) return t5::launch_cg<1>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st);
+  return t5::launch_cg<2>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st);
 }
 
 }  // namespace kvq

@@ -56,7 +56,7 @@ def one(mode, N, D, K, init):
     ms = e0.elapsed_time(e1) / reps
     print(json.dumps(dict(mode=mode, N=N, D=D, K=K, init=init, mismatch_vs_fp64=mism, beyond_tol=bad,
                           max_gap=float(gap_chosen.max()), ms=ms, tflops=2.0 * N * K * D / ms / 1e9,
-                          idx_min=int(idx.min()), idx_max=int(idx.max()), round_tf32=os.environ.get("KVQ_TMA_ROUND_TF32", "0"))),
+                          idx_min=int(idx.min()), idx_max=int(idx.max()))),
           flush=True)
 
 
@@ -78,11 +78,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         one(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6])
         sys.exit(0)
-    for env_round in ("0", "1"):
+    configs = [dict(KVQ_TF32_CTA_GROUP="2"), dict(KVQ_TF32_CTA_GROUP="1"), dict(KVQ_TF32_CTA_GROUP="2", KVQ_TMA_ROUND_TF32="0")]
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        configs = configs[:1]
+    for ci, cfg in enumerate(configs):
         for c in CASES:
-            if env_round == "1" and c[0] != "tf32":
+            if ci > 0 and (c[0] != "tf32" or c[1] < (1 << 16)):
                 continue
-            env = dict(os.environ, KVQ_TMA_ROUND_TF32=env_round)
+            env = dict(os.environ, **cfg)
             t0 = time.time()
             try:
                 r = subprocess.run([sys.executable, __file__, "one", *map(str, c)], env=env, capture_output=True,
@@ -92,4 +95,4 @@ if __name__ == "__main__":
                     tail = f"FAILED rc={r.returncode} case={c} :: " + (r.stdout + r.stderr)[-1500:]
             except subprocess.TimeoutExpired:
                 tail = f"TIMEOUT case={c}"
-            print(tail, f"[{time.time() - t0:.1f}s]", flush=True)
+            print(json.dumps(cfg), tail, f"[{time.time() - t0:.1f}s]", flush=True)
