@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python __graft_entry__.py > gpurun_out/build.log 2>&1 || { tail -20 gpurun_out/build.log; exit 1; }
+for K in 65536 8192; do
+  PCMD="python tools/probe.py one tf32 1048576 256 $K normal"
+  $PCMD > gpurun_out/probe_plain_$K.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:search_tf32 -s 1 -c 1 -o gpurun_out/search_2cta_K$K $PCMD > gpurun_out/ncu_full_$K.log 2>&1
+  echo "ncu K=$K rc=$?"; tail -2 gpurun_out/ncu_full_$K.log
+done
