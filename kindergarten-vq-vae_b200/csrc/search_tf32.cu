@@ -101,7 +101,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // arrive on a barrier that may live in the peer CTA (address from map_to_cta)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // default semantics (no cluster-scope release fence: no generic-memory data is published by this arrive, the
+  // TMEM reads it orders are covered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -177,18 +179,63 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B
   return d;
 }
-// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread, then wait for the load.
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread.  The load is asynchronous: the registers
+// may only be read after tmem_wait_ld on the same array (the "+r" operands make that a compiler-visible dependency).
+#define KVQ_R32(r) r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], \
+                   r[16], r[17], r[18], r[19], r[20], r[21], r[22], r[23], r[24], r[25], r[26], r[27], r[28], r[29], r[30], r[31]
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :: "memory");
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3
+  return r;
+}
+
+// One batch of 32 accumulator columns for one latent row: scores, their minimum by an FMNMX3 tree, and -- only when
+// the minimum beats the running best (rare after the first tiles) -- a scan for the FIRST column attaining it.
+// Equivalent to scanning the columns in increasing order with a strict '<': lowest index wins ties, NaN never wins.
+__device__ __forceinline__ void argmin_batch(const uint32_t (&acc)[32], const float4* __restrict__ e2v, uint32_t col_base,
+                                             float& best, uint32_t& bidx) {
+  float s[32];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 en = __ldg(e2v + j4);
+    s[j4 * 4 + 0] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 0]), en.x);
+    s[j4 * 4 + 1] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 1]), en.y);
+    s[j4 * 4 + 2] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 2]), en.z);
+    s[j4 * 4 + 3] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 3]), en.w);
+  }
+  float t[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) t[i] = fmin3(s[3 * i], s[3 * i + 1], s[3 * i + 2]);
+  t[10] = fminf(s[30], s[31]);
+  const float u0 = fmin3(t[0], t[1], t[2]), u1 = fmin3(t[3], t[4], t[5]), u2 = fmin3(t[6], t[7], t[8]);
+  const float u3 = fminf(t[9], t[10]);
+  const float m = fminf(fmin3(u0, u1, u2), u3);
+  if (m < best) {
+    best = m;
+    int j = 31;
+#pragma unroll
+    for (int jj = 30; jj >= 0; --jj) j = (s[jj] == m) ? jj : j;
+    bidx = col_base + (uint32_t)j;
+  }
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------
@@ -352,10 +399,8 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
       const int ks = (int)(item % p.ksplit);
       const int t_begin = ks * p.tiles_per_split;
       const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
-      float best[4];
-      uint32_t bidx[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { best[c] = INFINITY; bidx[c] = (uint32_t)(t_begin * BLOCK_N + half * 128 + c); }
+      float bv = INFINITY;
+      uint32_t bi = (uint32_t)(t_begin * BLOCK_N + half * 128);
 
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(bar_tm_full + 8 * acc, acc_phase);
@@ -363,36 +408,30 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
         const uint32_t col0 = (uint32_t)(t * BLOCK_N + half * 128);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * 128;
         const float4* e2v = reinterpret_cast<const float4*>(p.e2 + col0);
-#pragma unroll 1
-        for (int b = 0; b < 4; ++b) {
-          uint32_t r[32];
-          tmem_ld32(taddr + b * 32, r);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 en = __ldg(e2v + b * 8 + j4);
-            const float e[4] = {en.x, en.y, en.z, en.w};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float s = fmaf(-2.f, __uint_as_float(r[j4 * 4 + c]), e[c]);
-              if (s < best[c]) { best[c] = s; bidx[c] = col0 + b * 32 + j4 * 4 + c; }
-            }
-          }
-        }
+        // software pipeline over the four 32-column batches: the TMEM load of batch b+1 is in flight while batch b
+        // is reduced; the accumulator is handed back to the MMA as soon as the last load has landed.
+        uint32_t ra[32], rb[32];
+        tmem_ld32_async(taddr, ra);
+        tmem_wait_ld(ra);
+        tmem_ld32_async(taddr + 32, rb);
+        argmin_batch(ra, e2v, col0, bv, bi);
+        tmem_wait_ld(rb);
+        tmem_ld32_async(taddr + 64, ra);
+        argmin_batch(rb, e2v + 8, col0 + 32, bv, bi);
+        tmem_wait_ld(ra);
+        tmem_ld32_async(taddr + 96, rb);
+        argmin_batch(ra, e2v + 16, col0 + 64, bv, bi);
+        tmem_wait_ld(rb);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if constexpr (CG == 2) mbar_arrive_cluster(map_to_cta(bar_tm_empty + 8 * acc, 0));
           else mbar_arrive(bar_tm_empty + 8 * acc);
         }
+        argmin_batch(rb, e2v + 24, col0 + 96, bv, bi);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      // merge the four chains (lexicographic (score, index): lowest index wins ties)
-      float bv = best[0];
-      uint32_t bi = bidx[0];
-#pragma unroll
-      for (int c = 1; c < 4; ++c)
-        if (best[c] < bv || (best[c] == bv && bidx[c] < bi)) { bv = best[c]; bi = bidx[c]; }
       // merge the two column halves through shared memory
       if (half == 1) { merge_val[row_in_tile] = bv; merge_idx[row_in_tile] = bi; }
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");

@@ -82,14 +82,20 @@ __global__ void __launch_bounds__(128, 1) floor_kernel(long long* cycles, int it
 
 template <int KIND, int N, int TS>
 void run(const char* name) {
-  constexpr int KSTEPS = 16;
-  long long* d; cudaMalloc(&d, 8);
+  constexpr int KSTEPS = 8;
+  fprintf(stderr, "[%s] start\n", name); fflush(stderr);
+  long long* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, 8);
+  fprintf(stderr, "[%s] malloc %d\n", name, (int)e); fflush(stderr);
   auto kern = floor_kernel<KIND, N, TS, KSTEPS>;
   const int smem = 162 * 1024;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  fprintf(stderr, "[%s] attr %d\n", name, (int)e); fflush(stderr);
   const int iters = 2000;
   kern<<<148, 128, smem>>>(d, 10);
-  cudaDeviceSynchronize();
+  e = cudaDeviceSynchronize();
+  fprintf(stderr, "[%s] warm %d %s\n", name, (int)e, cudaGetErrorString(e)); fflush(stderr);
+  if (e != cudaSuccess) return;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
   kern<<<148, 128, smem>>>(d, iters);
@@ -106,6 +112,9 @@ void run(const char* name) {
 }
 
 int main() {
+  setvbuf(stdout, nullptr, _IONBF, 0);
+  int ndev = 0; cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  fprintf(stderr, "devices %d err %d\n", ndev, (int)e0); fflush(stderr);
   run<0, 256, 0>("tf32 SS M128 N256");
   run<0, 128, 0>("tf32 SS M128 N128");
   run<0, 64, 0>("tf32 SS M128 N64");
