@@ -86,6 +86,16 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// one lane of the (converged) warp: the same lane every time, so commits track the MMAs that lane issued
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -181,8 +191,6 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 }
 // 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread.  The load is asynchronous: the registers
 // may only be read after tmem_wait_ld on the same array (the "+r" operands make that a compiler-visible dependency).
-#define KVQ_R32(r) r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], \
-                   r[16], r[17], r[18], r[19], r[20], r[21], r[22], r[23], r[24], r[25], r[26], r[27], r[28], r[29], r[30], r[31]
 __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -310,27 +318,31 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
 
   if (warp == 0) {
     // =========================== TMA producer (every CTA) ===========================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
-      // completion bytes of both CTAs are counted on the leader's barriers
-      const uint32_t a_full_sig = (CG == 2) ? map_to_cta(bar_a_full, 0) : bar_a_full;
-      for (int64_t item = first_item; item < p.n_items; item += item_stride) {
-        const int64_t m_group = item / p.ksplit;
-        const int ks = (int)(item % p.ksplit);
-        const int m0 = (int)((m_group * CG + cta_rank) * BLOCK_M);
-        const int t_begin = ks * p.tiles_per_split;
-        const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
-        if (p.resident) {
-          mbar_wait(bar_a_empty, a_phase ^ 1);          // previous item's MMAs have finished reading the tile
+    // The whole warp walks the loop (warp-uniform control flow); one elected lane issues the copies.
+    uint32_t stage = 0, phase = 0, a_phase = 0;
+    // completion bytes of both CTAs are counted on the leader's barriers
+    const uint32_t a_full_sig = (CG == 2) ? map_to_cta(bar_a_full, 0) : bar_a_full;
+    for (int64_t item = first_item; item < p.n_items; item += item_stride) {
+      const int64_t m_group = item / p.ksplit;
+      const int ks = (int)(item % p.ksplit);
+      const int m0 = (int)((m_group * CG + cta_rank) * BLOCK_M);
+      const int t_begin = ks * p.tiles_per_split;
+      const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+      if (p.resident) {
+        mbar_wait(bar_a_empty, a_phase ^ 1);          // previous item's MMAs have finished reading the tile
+        if (elect_one()) {
           if (leader) mbar_expect_tx(bar_a_full, a_bytes * CG);
           for (int kb = 0; kb < p.num_kblocks; ++kb)
             tma_load_2d<CG>(a_region + kb * A_KBLOCK_BYTES, &tmap_z, kb * BLOCK_K, m0, a_full_sig);
-          a_phase ^= 1;
         }
-        for (int t = t_begin; t < t_end; ++t) {
-          const int n0 = t * BLOCK_N + (int)cta_rank * B_ROWS;
-          for (int kb = 0; kb < p.num_kblocks; ++kb) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        __syncwarp();
+        a_phase ^= 1;
+      }
+      for (int t = t_begin; t < t_end; ++t) {
+        const int n0 = t * BLOCK_N + (int)cta_rank * B_ROWS;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (elect_one()) {
             const uint32_t sbase = ring + stage * stage_bytes;
             const uint32_t full_own = bar_full + 8 * stage;
             const uint32_t full_sig = (CG == 2) ? map_to_cta(full_own, 0) : full_own;
@@ -341,15 +353,21 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
             } else {
               tma_load_2d<CG>(sbase, &tmap_e, kb * BLOCK_K, n0, full_sig);
             }
-            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (leader CTA, one lane) ===========================
-    if (lane == 0 && leader) {
+    // =========================== MMA issuer (leader CTA) ===========================
+    // Warp-uniform loop, one elected lane issues tcgen05.mma / tcgen05.commit.  (Putting the whole loop under
+    // `if (lane == 0)` made the compiler wrap every MMA in a per-active-thread serialisation loop -- ~100
+    // instructions per k-block on the critical issue path, measured as the limiter at 70 % tensor-pipe active.)
+    if (leader) {
       uint32_t stage = 0, phase = 0, a_phase = 0, acc = 0, acc_phase = 0;
+      // descriptor constants: everything but the 14-bit start address
+      const uint64_t desc_hi = smem_desc(0);
       for (int64_t item = first_item; item < p.n_items; item += item_stride) {
         const int ks = (int)(item % p.ksplit);
         const int t_begin = ks * p.tiles_per_split;
@@ -366,27 +384,33 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
           for (int kb = 0; kb < p.num_kblocks; ++kb) {
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
-            const uint32_t sbase = ring + stage * stage_bytes;
-            const uint32_t a_addr = p.resident ? (a_region + kb * A_KBLOCK_BYTES) : sbase;
-            const uint32_t b_addr = p.resident ? sbase : (sbase + A_KBLOCK_BYTES);
-            const uint64_t adesc = smem_desc(a_addr);
-            const uint64_t bdesc = smem_desc(b_addr);
+            if (elect_one()) {
+              const uint32_t sbase = ring + stage * stage_bytes;
+              const uint32_t a_addr = p.resident ? (a_region + kb * A_KBLOCK_BYTES) : sbase;
+              const uint32_t b_addr = p.resident ? sbase : (sbase + A_KBLOCK_BYTES);
+              const uint64_t adesc = desc_hi | (uint64_t)((a_addr & 0x3ffffu) >> 4);
+              const uint64_t bdesc = desc_hi | (uint64_t)((b_addr & 0x3ffffu) >> 4);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-              tc_mma_tf32<CG>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                tc_mma_tf32<CG>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+              }
+              tc_commit<CG>(bar_empty + 8 * stage);           // stage reusable once these MMAs retire
             }
-            tc_commit<CG>(bar_empty + 8 * stage);             // stage reusable once these MMAs retire
+            __syncwarp();
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
-          tc_commit<CG>(bar_tm_full + 8 * acc);               // accumulator complete -> epilogues of the pair
+          if (elect_one()) tc_commit<CG>(bar_tm_full + 8 * acc);   // accumulator complete -> epilogues of the pair
+          __syncwarp();
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
-        if (p.resident) tc_commit<CG>(bar_a_empty);           // latent tiles may be overwritten
+        if (p.resident) {
+          if (elect_one()) tc_commit<CG>(bar_a_empty);        // latent tiles may be overwritten
+          __syncwarp();
+        }
       }
     }
-    __syncwarp();
   } else {
     // =========================== argmin epilogue (every CTA) ===========================
     const int ew = warp - 2;
