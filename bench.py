@@ -257,12 +257,34 @@ def run_kvq(args):
     pk = peaks()
     sustained = args.steps * ms_per_step > 1000.0
     tf32_peak = (pk["bf16_tflops_sustained"] if sustained else pk["bf16_tflops"]) / 2.0
+    # library tf32 GEMM on this GPU, measured live (torch.matmul 8192^3, best of 5): context for the search kernel
+    cublas_tf32 = None
+    if rank == 0 and not args.no_cublas:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device=dev); b = torch.randn(8192, 8192, device=dev)
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(5):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(); a @ b; c1.record(); torch.cuda.synchronize()
+            best = min(best, c0.elapsed_time(c1))
+        cublas_tf32 = 2 * 8192 ** 3 / best / 1e9
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        del a, b
     roof = None
     if prof["search"]:
         flops = 2.0 * n_rows * K * D
         ach = flops / (prof["search"] * 1e-3) / 1e12
         roof = {"kernel": "search_tf32_kernel (tcgen05 distance+argmin)", "bound": "tensor", "achieved": ach,
-                "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+                "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the ncu --set full
+                # capture profiles/r01/ncu_search_v3.summary.csv (4.525 GB + 24.5 MB); algorithmic HBM bytes are 1.15 GB
+                # -- the 64 MB codebook is re-read from HBM on each of the ~55 sweeps per SM pair (107 GB/s, irrelevant
+                # to a tensor-bound kernel)
+                "traffic": 4.549e9 if (n_rows == 1 << 20 and K == 65536) else None,
+                "cublas_tf32_tflops_live": cublas_tf32,
                 "peak_source": f"{pk['source']} bf16 dense {'sustained' if sustained else 'burst'} / 2 "
                                "(tf32 runs at half the bf16 rate; tf32 itself is not in MEASURED_PEAKS.json)",
                 "algorithmic_flops_per_launch": flops, "ms_per_launch": prof["search"]}
@@ -301,7 +323,7 @@ def run_kvq(args):
                        "codebook_init": "data-scale: N(0,1) rows + 0.1 noise"},
             "roofline": roof, "roofline_other_kernels": others, "kernel_ms": prof,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "loss": float(loss), "perplexity": float(perp),
+            "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -374,6 +396,7 @@ def main():
     ap.add_argument("--impl", default="kvq", choices=["kvq", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cublas", action="store_true")
     ap.add_argument("--chunk-rows", type=int, default=131072)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "kvq":
