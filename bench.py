@@ -353,37 +353,24 @@ def measure_e2e(torch, dist, F, vq, z, gz, E, dev, world, args):
         api = "kvq_forward_backward_host (C ABI, pinned host buffers, chunked copy/compute overlap)"
         F._lib.load().kvq_host_release()
     else:
-        one = torch.ones((), device=dev)
-        outs = dict(z_q=torch.empty(n_rows, D, pin_memory=True), dz=torch.empty(n_rows, D, pin_memory=True),
-                    idx=torch.empty(n_rows, dtype=torch.int64, pin_memory=True), dE=torch.empty(K, D, pin_memory=True),
-                    scal=torch.empty(2, pin_memory=True))
-
-        def host_step():
-            zd = zh.to(dev, non_blocking=True).view(n_rows // 64, 64, D).requires_grad_(True)
-            gd = gh.to(dev, non_blocking=True).view(n_rows // 64, 64, D)
-            vq.embedding.weight.data.copy_(Eh, non_blocking=True)
-            vq.embedding.weight.grad = None
-            loss, z_q, perp, _, idx = vq.forward(zd, dev)
-            torch.autograd.backward([loss, z_q], [one, gd])
-            outs["z_q"].copy_(z_q.detach().view(n_rows, D), non_blocking=True)
-            outs["dz"].copy_(zd.grad.view(n_rows, D), non_blocking=True)
-            outs["idx"].copy_(idx.view(-1), non_blocking=True)
-            outs["dE"].copy_(vq.embedding.weight.grad, non_blocking=True)
-            outs["scal"][0:1].copy_(loss.detach().view(1), non_blocking=True)
-            outs["scal"][1:2].copy_(perp.view(1), non_blocking=True)
-            torch.cuda.synchronize()
-
-        host_step()
+        out = None
+        n_global = n_rows * world
+        for _ in range(2):
+            out = F.forward_backward_host_sharded(zh, Eh, gh, 1.0, BETA, n_global, mode="tf32",
+                                                  rows_per_chunk=args.chunk_rows, out=out)
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            host_step()
+            out = F.forward_backward_host_sharded(zh, Eh, gh, 1.0, BETA, n_global, mode="tf32",
+                                                  rows_per_chunk=args.chunk_rows, out=out)
         dist.barrier()
         dt = (time.perf_counter() - t0) / steps
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        api = "BatchShardedVectorQuantizer.forward/backward with pinned-host inputs and outputs (per rank)"
+        api = ("kvq_forward_backward_host_sharded per rank (C ABI, pinned host buffers, chunked copy/compute overlap) "
+               "+ NCCL all-reduce of dE, histogram, loss partial")
+        F._lib.load().kvq_host_release()
     return {"value": n_rows * world / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": dt * 1e3, "steps": steps, "api": api}
 
@@ -397,7 +384,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cublas", action="store_true")
-    ap.add_argument("--chunk-rows", type=int, default=131072)
+    ap.add_argument("--chunk-rows", type=int, default=75776)  # 4 full waves of 74 CTA pairs x 256 rows
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "kvq":
         args.warmup = 3          # timing rule: at least three warm-up steps

@@ -159,6 +159,15 @@ int kvq_forward_backward_host(const float* z_host, const float* E_host, const fl
                               int64_t N, int D, int64_t K, float beta, int mode,
                               float* z_q_host, int64_t* idx_host, float* loss_host, float* perplexity_host,
                               float* dz_host, float* dE_host, int64_t rows_per_chunk);
+/* Batch-sharded form of the call above (one process per GPU): this rank's rows in and out through host buffers, but
+ * the three quantities that span ranks are left as per-rank PARTIALS in caller-provided DEVICE buffers, already
+ * normalised by n_global: sq_sum_dev (1 double), hist_dev (K int32), dE_dev (K*D float).  The caller all-reduces
+ * them (SUM, e.g. NCCL), then calls kvq_finalize for loss / perplexity. */
+int kvq_forward_backward_host_sharded(const float* z_host, const float* E_host, const float* g_zq_host,
+                                      float g_loss_host, int64_t N, int D, int64_t K, float beta, int mode,
+                                      int64_t n_global, float* z_q_host, int64_t* idx_host, float* dz_host,
+                                      double* sq_sum_dev, int32_t* hist_dev, float* dE_dev, int64_t rows_per_chunk);
+
 /* Frees the device staging buffers kvq_forward_backward_host caches between calls. */
 int kvq_host_release(void);
 

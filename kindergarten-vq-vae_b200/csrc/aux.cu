@@ -143,12 +143,20 @@ int kvq_host_release(void) {
   return KVQ_OK;
 }
 
-int kvq_forward_backward_host(const float* z_h, const float* E_h, const float* g_h, float g_loss_h, int64_t N, int D,
-                              int64_t K, float beta, int mode, float* zq_h, int64_t* idx_h, float* loss_h,
-                              float* perp_h, float* dz_h, float* dE_h, int64_t rows_per_chunk) {
+}  // extern "C"
+
+// Shared body of the two host-buffer entry points.  In sharded mode (sq_dev / hist_dev / dE_dev given) the
+// reductions that span ranks are left as per-rank partials in the caller's DEVICE buffers, normalised by n_global.
+static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, float g_loss_h, int64_t N, int D,
+                         int64_t K, float beta, int mode, float* zq_h, int64_t* idx_h, float* loss_h,
+                         float* perp_h, float* dz_h, float* dE_h, int64_t rows_per_chunk, int64_t n_global,
+                         double* sq_dev, int32_t* hist_dev, float* dE_dev) {
+  const bool sharded = sq_dev != nullptr;
   int rc = check_device(); if (rc) return rc;
-  KVQ_REQUIRE(z_h && E_h && g_h && zq_h && idx_h && loss_h && perp_h && dz_h && dE_h, KVQ_ERR_ARG,
-              "kvq_forward_backward_host: null pointer");
+  KVQ_REQUIRE(z_h && E_h && g_h && zq_h && idx_h && dz_h, KVQ_ERR_ARG, "kvq_forward_backward_host: null pointer");
+  KVQ_REQUIRE(sharded ? (hist_dev && dE_dev) : (loss_h && perp_h && dE_h), KVQ_ERR_ARG,
+              "kvq_forward_backward_host: null output pointer");
+  KVQ_REQUIRE(n_global >= N, KVQ_ERR_ARG, "kvq_forward_backward_host: n_global < N");
   KVQ_REQUIRE(N >= 1 && K >= 1 && D >= 4 && D % 4 == 0 && D <= 1024, KVQ_ERR_SHAPE,
               "kvq_forward_backward_host: bad shape N=%lld D=%d K=%lld", (long long)N, D, (long long)K);
   if (rows_per_chunk <= 0) rows_per_chunk = 131072;
@@ -167,7 +175,10 @@ int kvq_forward_backward_host(const float* z_h, const float* E_h, const float* g
   char* wp = static_cast<char*>(hp.ws);
   float* e2 = reinterpret_cast<float*>(wp);
   long long* keys = reinterpret_cast<long long*>(wp + align_up((size_t)K_pad * 4, 256));
-  double* sq_sum = reinterpret_cast<double*>(wp + align_up((size_t)K_pad * 4, 256) + align_up((size_t)N * 8, 256));
+  double* sq_sum = sharded ? sq_dev
+                           : reinterpret_cast<double*>(wp + align_up((size_t)K_pad * 4, 256) + align_up((size_t)N * 8, 256));
+  int32_t* hist = sharded ? hist_dev : hp.hist;
+  float* dE = sharded ? dE_dev : hp.dE;
 
   cudaEvent_t* ev_in = new cudaEvent_t[chunks];
   cudaEvent_t* ev_done = new cudaEvent_t[chunks];
@@ -204,7 +215,7 @@ int kvq_forward_backward_host(const float* z_h, const float* E_h, const float* g
   KVQ_TRYC(cudaStreamWaitEvent(hp.s_cmp, ev_E, 0));
   KVQ_TRY(launch_code_norms(hp.E, K, D, e2, K_pad, hp.s_cmp));
   KVQ_TRYC(cudaMemsetAsync(sq_sum, 0, sizeof(double), hp.s_cmp));
-  KVQ_TRYC(cudaMemsetAsync(hp.hist, 0, (size_t)K * 4, hp.s_cmp));
+  KVQ_TRYC(cudaMemsetAsync(hist, 0, (size_t)K * 4, hp.s_cmp));
   for (int64_t c = 0; c < chunks && status == KVQ_OK; ++c) {
     const int64_t r0 = c * rows_per_chunk, rows = (N - r0 < rows_per_chunk) ? (N - r0) : rows_per_chunk;
     KVQ_TRYC(cudaStreamWaitEvent(hp.s_cmp, ev_in[c], 0));
@@ -212,11 +223,11 @@ int kvq_forward_backward_host(const float* z_h, const float* E_h, const float* g
       KVQ_TRY(launch_search_tf32(hp.z + r0 * D, hp.E, e2, rows, D, K, 0, hp.idx + r0, keys + r0, 0, hp.s_cmp));
     else
       KVQ_TRY(launch_search_fp32(hp.z + r0 * D, hp.E, e2, rows, D, K, 0, hp.idx + r0, keys + r0, 0, hp.s_cmp));
-    KVQ_TRY(launch_quantize(hp.z + r0 * D, hp.E, hp.idx + r0, rows, D, K, 0, 0, hp.zq + r0 * D, sq_sum, hp.hist, hp.s_cmp));
+    KVQ_TRY(launch_quantize(hp.z + r0 * D, hp.E, hp.idx + r0, rows, D, K, 0, 0, hp.zq + r0 * D, sq_sum, hist, hp.s_cmp));
     // dz depends only on this chunk's rows and the (host-given) loss weight: compute it now so that its
     // device->host copy overlaps the search of the next chunk.
-    KVQ_TRY(launch_backward(hp.z + r0 * D, hp.E, hp.idx + r0, nullptr, hp.g + r0 * D, hp.scal + 2, rows, D, K, 0, beta, N,
-                            hp.dz + r0 * D, nullptr, nullptr, 0, hp.s_cmp));
+    KVQ_TRY(launch_backward(hp.z + r0 * D, hp.E, hp.idx + r0, nullptr, hp.g + r0 * D, hp.scal + 2, rows, D, K, 0, beta,
+                            n_global, hp.dz + r0 * D, nullptr, nullptr, 0, hp.s_cmp));
     KVQ_TRYC(cudaEventRecord(ev_done[c], hp.s_cmp));
     // outputs of this chunk
     KVQ_TRYC(cudaStreamWaitEvent(hp.s_out, ev_done[c], 0));
@@ -225,13 +236,15 @@ int kvq_forward_backward_host(const float* z_h, const float* E_h, const float* g
     KVQ_TRYC(cudaMemcpyAsync(idx_h + r0, hp.idx + r0, (size_t)rows * 8, cudaMemcpyDeviceToHost, hp.s_out));
   }
   if (status == KVQ_OK) {
-    KVQ_TRY(launch_finalize(sq_sum, hp.hist, N, D, K, beta, hp.scal, hp.scal + 1, hp.s_cmp));
-    // codebook gradient over all rows (bucketed by code); dz was already produced per chunk
-    KVQ_TRY(launch_backward(hp.z, hp.E, hp.idx, hp.hist, nullptr, hp.scal + 2, N, D, K, 0, beta, N, nullptr, hp.dE, hp.ws,
+    // codebook gradient over all local rows (bucketed by code); dz was already produced per chunk
+    KVQ_TRY(launch_backward(hp.z, hp.E, hp.idx, hist, nullptr, hp.scal + 2, N, D, K, 0, beta, n_global, nullptr, dE, hp.ws,
                             hp.cap_ws, hp.s_cmp));
-    KVQ_TRYC(cudaMemcpyAsync(loss_h, hp.scal, 4, cudaMemcpyDeviceToHost, hp.s_cmp));
-    KVQ_TRYC(cudaMemcpyAsync(perp_h, hp.scal + 1, 4, cudaMemcpyDeviceToHost, hp.s_cmp));
-    KVQ_TRYC(cudaMemcpyAsync(dE_h, hp.dE, (size_t)K * D * 4, cudaMemcpyDeviceToHost, hp.s_cmp));
+    if (!sharded) {
+      KVQ_TRY(launch_finalize(sq_sum, hist, N, D, K, beta, hp.scal, hp.scal + 1, hp.s_cmp));
+      KVQ_TRYC(cudaMemcpyAsync(loss_h, hp.scal, 4, cudaMemcpyDeviceToHost, hp.s_cmp));
+      KVQ_TRYC(cudaMemcpyAsync(perp_h, hp.scal + 1, 4, cudaMemcpyDeviceToHost, hp.s_cmp));
+      KVQ_TRYC(cudaMemcpyAsync(dE_h, dE, (size_t)K * D * 4, cudaMemcpyDeviceToHost, hp.s_cmp));
+    }
   }
   KVQ_TRYC(cudaStreamSynchronize(hp.s_in));
   KVQ_TRYC(cudaStreamSynchronize(hp.s_cmp));
@@ -242,6 +255,24 @@ int kvq_forward_backward_host(const float* z_h, const float* E_h, const float* g
   cudaEventDestroy(ev_E); cudaEventDestroy(ev_final);
   delete[] ev_in; delete[] ev_done;
   return status;
+}
+
+extern "C" {
+
+int kvq_forward_backward_host(const float* z_h, const float* E_h, const float* g_h, float g_loss_h, int64_t N, int D,
+                              int64_t K, float beta, int mode, float* zq_h, int64_t* idx_h, float* loss_h,
+                              float* perp_h, float* dz_h, float* dE_h, int64_t rows_per_chunk) {
+  return host_pipeline(z_h, E_h, g_h, g_loss_h, N, D, K, beta, mode, zq_h, idx_h, loss_h, perp_h, dz_h, dE_h,
+                       rows_per_chunk, N, nullptr, nullptr, nullptr);
+}
+
+int kvq_forward_backward_host_sharded(const float* z_h, const float* E_h, const float* g_h, float g_loss_h, int64_t N,
+                                      int D, int64_t K, float beta, int mode, int64_t n_global, float* zq_h,
+                                      int64_t* idx_h, float* dz_h, double* sq_sum_dev, int32_t* hist_dev, float* dE_dev,
+                                      int64_t rows_per_chunk) {
+  KVQ_REQUIRE(sq_sum_dev && hist_dev && dE_dev, KVQ_ERR_ARG, "kvq_forward_backward_host_sharded: null device buffer");
+  return host_pipeline(z_h, E_h, g_h, g_loss_h, N, D, K, beta, mode, zq_h, idx_h, nullptr, nullptr, dz_h, nullptr,
+                       rows_per_chunk, n_global, sq_sum_dev, hist_dev, dE_dev);
 }
 
 }  // extern "C"

@@ -212,3 +212,38 @@ def forward_backward_host(z: torch.Tensor, E: torch.Tensor, g_zq: torch.Tensor, 
         out["dz"].data_ptr(), out["dE"].data_ptr(), rows_per_chunk), "kvq_forward_backward_host")
     out["loss"], out["perplexity"] = out["scal"][0], out["scal"][1]
     return out
+
+
+def forward_backward_host_sharded(z: torch.Tensor, E: torch.Tensor, g_zq: torch.Tensor, g_loss: float, beta: float,
+                                  n_global: int, *, group=None, mode: str = "auto", rows_per_chunk: int = 0, out=None):
+    """Batch-sharded end-to-end step with HOST tensors: this rank's rows through the chunked copy/compute pipeline,
+    then one all-reduce(SUM) of [dE | histogram | squared-residual sum] partials over `group` and the finalisation.
+    Returns dict of host tensors (z_q, idx, dz local rows; dE, loss, perplexity global)."""
+    import torch.distributed as dist
+    for name, t in (("z", z), ("E", E), ("g_zq", g_zq)):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError(f"{name} must be a contiguous fp32 host tensor")
+    N, D = z.shape
+    K = E.shape[0]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if out is None:
+        out = dict(z_q=torch.empty(N, D, pin_memory=True), idx=torch.empty(N, dtype=torch.int64, pin_memory=True),
+                   dz=torch.empty(N, D, pin_memory=True), dE=torch.empty(K, D, pin_memory=True),
+                   scal=torch.empty(2, pin_memory=True),
+                   dE_dev=torch.empty(K, D, device=dev), hist_dev=torch.empty(K, dtype=torch.int32, device=dev),
+                   sq_dev=torch.empty(1, dtype=torch.float64, device=dev))
+    check(_lib.load().kvq_forward_backward_host_sharded(
+        z.data_ptr(), E.data_ptr(), g_zq.data_ptr(), float(g_loss), N, D, K, float(beta), SEARCH_MODES[mode], n_global,
+        out["z_q"].data_ptr(), out["idx"].data_ptr(), out["dz"].data_ptr(), out["sq_dev"].data_ptr(),
+        out["hist_dev"].data_ptr(), out["dE_dev"].data_ptr(), rows_per_chunk), "kvq_forward_backward_host_sharded")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(out["dE_dev"], group=group)
+        dist.all_reduce(out["hist_dev"], group=group)
+        dist.all_reduce(out["sq_dev"], group=group)
+    loss, perp = finalize(out["sq_dev"], out["hist_dev"], n_global, D, beta)
+    out["dE"].copy_(out["dE_dev"], non_blocking=True)
+    out["scal"][0:1].copy_(loss.view(1), non_blocking=True)
+    out["scal"][1:2].copy_(perp.view(1), non_blocking=True)
+    torch.cuda.synchronize()
+    out["loss"], out["perplexity"] = out["scal"][0], out["scal"][1]
+    return out

@@ -86,4 +86,10 @@ def test_host_end_to_end_matches_device_path():
         assert (out["dE"] - dE.cpu()).abs().max() <= 1e-5 * dE.abs().max()
     ref = O.forward_fp32(z, E, 0.25)
     assert O.index_parity(out["idx"], ref.idx, z, E).unexcused == 0
+    # sharded entry point on one rank (no process group): same pipeline, partials finalised by the caller
+    out2 = F.forward_backward_host_sharded(z, E, g, 1.25, 0.25, N, mode="tf32", rows_per_chunk=1024)
+    assert torch.equal(out2["idx"], out["idx"]) and torch.equal(out2["z_q"], out["z_q"]) and torch.equal(out2["dz"], out["dz"])
+    assert abs(float(out2["loss"]) - float(out["loss"])) <= 1e-6 * float(out["loss"])
+    assert abs(float(out2["perplexity"]) - float(out["perplexity"])) <= 1e-6 * float(out["perplexity"])
+    assert (out2["dE"] - out["dE"]).abs().max() <= 1e-6 * out["dE"].abs().max()
     F._lib.load().kvq_host_release()
