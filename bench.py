@@ -248,6 +248,23 @@ def run_kvq(args):
     ms_per_step = float(t.item()) / args.steps
     value = n_rows * world / (ms_per_step * 1e-3)
 
+    # ---- result check on the measured configuration: sampled rows against an fp64 evaluation on the device -------
+    parity = None
+    if rank == 0:
+        with torch.no_grad():
+            _, _, _, _, idx_chk = vq.forward(z3, dev)
+            rows = torch.arange(0, n_rows, n_rows // 2048, device=dev)[:2048]
+            zs = z[rows].double(); Ed = E.double()
+            d = (Ed * Ed).sum(1) - 2.0 * zs @ Ed.t()
+            best = d.argmin(1)
+            chosen = d.gather(1, idx_chk.view(-1)[rows, None]).squeeze(1)
+            gap = chosen - d.min(1).values
+            tol = 2.0 ** -9 * zs.norm(dim=1) * Ed.norm(dim=1).max()
+            parity = {"rows_checked": int(rows.numel()), "index_mismatch_vs_fp64": int((best != idx_chk.view(-1)[rows]).sum()),
+                      "beyond_tf32_tolerance": int((gap > tol).sum()), "max_gap_over_tolerance": float((gap / tol).max()),
+                      "tolerance": "2^-9 * |z_i| * max_k |E_k| on the fp64 squared-distance gap (DESIGN.md section 3)"}
+            del d, zs, Ed
+
     # ---- end to end with host buffers (H2D + compute + D2H inside the timed region) --------------------
     e2e = None
     if not args.no_e2e:
@@ -323,7 +340,7 @@ def run_kvq(args):
                        "codebook_init": "data-scale: N(0,1) rows + 0.1 noise"},
             "roofline": roof, "roofline_other_kernels": others, "kernel_ms": prof,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp),
+            "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp), "index_parity": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -133,6 +133,17 @@ int kvq_backward(const float* z, const float* E, const int64_t* idx, const int32
 int kvq_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t N, int D,
                    int64_t n_global, float* dz, kvq_stream_t stream);
 
+/* Code-usage histogram of an index vector: hist[k] = #{i : idx[i] == k_offset + k}  (hist is overwritten). */
+int kvq_histogram(const int64_t* idx, int64_t N, int64_t K, int64_t k_offset, int32_t* hist, kvq_stream_t stream);
+
+/* One Lloyd update for the data-driven codebook initialisation (models/shelgon3/vq_codebook_init_weights.py:85,
+ * scipy.cluster.vq.kmeans2): new_centroids[k] = mean of the latents with idx == k; clusters without members keep
+ * old_centroids[k] (kmeans2's missing='warn' behaviour).  `hist` = kvq_histogram(idx).  Same bucketed pass as the
+ * backward's scatter-add, same workspace size. */
+int kvq_kmeans_update(const float* z, const int64_t* idx, const int32_t* hist, int64_t N, int D, int64_t K,
+                      const float* old_centroids, float* new_centroids, void* workspace, size_t workspace_bytes,
+                      kvq_stream_t stream);
+
 /* Dense one-hot `min_encodings` (N,K) fp32.  VectorQuantizer.py:67-68.  Only on request: 4*N*K bytes. */
 int kvq_onehot(const int64_t* idx, int64_t N, int64_t K, float* out, kvq_stream_t stream);
 

@@ -38,6 +38,8 @@ SIGNATURES = {
     "kvq_backward": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_int64, c_float, c_int64, _P, _P,
                              _P, c_size_t, _P]),
     "kvq_dz_from_zq": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int64, _P, _P]),
+    "kvq_histogram": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),
+    "kvq_kmeans_update": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, _P, _P, _P, c_size_t, _P]),
     "kvq_onehot": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "kvq_seq_acc": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),
     "kvq_replace_pct_rand_values": (c_int, [_P, c_int64, c_double, c_int64, c_int64, c_uint64, _P, _P]),

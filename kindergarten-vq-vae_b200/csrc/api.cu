@@ -252,6 +252,22 @@ int kvq_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const fl
   return launch_dz_from_zq(z, z_q, g_zq, g_loss, N * D, 1.0 / ((double)n_global * (double)D), dz, (cudaStream_t)stream);
 }
 
+int kvq_histogram(const int64_t* idx, int64_t N, int64_t K, int64_t k_offset, int32_t* hist, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  KVQ_REQUIRE(idx && hist && N >= 0 && K >= 1, KVQ_ERR_ARG, "kvq_histogram: bad arguments");
+  return launch_histogram(idx, N, K, k_offset, hist, (cudaStream_t)stream);
+}
+
+int kvq_kmeans_update(const float* z, const int64_t* idx, const int32_t* hist, int64_t N, int D, int64_t K,
+                      const float* old_centroids, float* new_centroids, void* ws, size_t ws_bytes, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  rc = check_shape("kvq_kmeans_update", N, D, K); if (rc) return rc;
+  KVQ_REQUIRE(z && idx && hist && old_centroids && new_centroids && ws, KVQ_ERR_ARG, "kvq_kmeans_update: null pointer");
+  KVQ_REQUIRE(old_centroids != new_centroids, KVQ_ERR_ARG, "kvq_kmeans_update: old and new centroids must differ");
+  KVQ_REQUIRE(((uintptr_t)ws & 255) == 0, KVQ_ERR_WORKSPACE, "kvq_kmeans_update: workspace must be 256-byte aligned");
+  return launch_kmeans_update(z, idx, hist, N, D, K, old_centroids, new_centroids, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 int kvq_onehot(const int64_t* idx, int64_t N, int64_t K, float* out, kvq_stream_t stream) {
   int rc = check_device(); if (rc) return rc;
   KVQ_REQUIRE(idx && out && N >= 0 && K >= 1, KVQ_ERR_ARG, "kvq_onehot: bad arguments");

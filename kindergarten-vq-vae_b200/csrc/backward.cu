@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) bucket_fill_kernel(const int64_t* __restr
 }
 
 // ---- 3. segmented pass -----------------------------------------------------------------------------
-template <int VPL>
+template <int VPL, bool MEAN = false>
 __device__ __forceinline__ void flush_bucket(float4 (&acc)[VPL], int code, int p0, int p1, float c2,
                                              const int32_t* __restrict__ offsets, int32_t total, int64_t K,
                                              float* __restrict__ dE, int D, int lane) {
@@ -147,6 +147,7 @@ __device__ __forceinline__ void flush_bucket(float4 (&acc)[VPL], int code, int p
   const int seg_lo = offsets[code];
   const int seg_hi = (code + 1 < K) ? offsets[code + 1] : total;
   const bool whole = (seg_lo >= p0) && (seg_hi <= p1);
+  if (MEAN) c2 = 1.0f / (float)(seg_hi - seg_lo);   // centroid = sum / count; partial sums of a cut bucket scale alike
   float4* row = reinterpret_cast<float4*>(dE + (int64_t)code * D);
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
@@ -241,6 +242,89 @@ __global__ void __launch_bounds__(256) segmented_backward_kernel(
     }
   }
   if (cur >= 0 && dE) flush_bucket<VPL>(acc, cur, p0, p1, c2, offsets, total, K, dE, D, lane);
+}
+
+// k-means centroid update on the same bucketed layout: centroid[k] = mean of the latents assigned to k.
+// (device replacement of scipy kmeans2's update_cluster_means,
+//  models/shelgon3/vq_codebook_init_weights.py:85.)
+template <int VPL>
+__global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ z, const int2* __restrict__ slots,
+                                                           const int32_t* __restrict__ offsets,
+                                                           const int32_t* __restrict__ total_p, int D, int64_t K,
+                                                           float* __restrict__ centroids) {
+  constexpr int R = (VPL <= 2) ? 4 : ((VPL <= 4) ? 2 : 1);
+  const int lane = threadIdx.x & 31;
+  const int32_t total = *total_p;
+  const int64_t p0l = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (p0l >= total) return;
+  const int p0 = (int)p0l;
+  const int count = min(32, total - p0);
+  const int p1 = p0 + count;
+  const int nvec = D >> 2;
+  int2 mine = make_int2(0, -1);
+  if (lane < count) mine = slots[p0 + lane];
+  float4 acc[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur = -1;
+  for (int r0 = 0; r0 < count; r0 += R) {
+    float4 zv[R][VPL];
+    int codes[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = __shfl_sync(0xffffffffu, mine.x, (r0 + r) & 31);
+      codes[r] = __shfl_sync(0xffffffffu, mine.y, (r0 + r) & 31);
+      const float4* zr = reinterpret_cast<const float4*>(z + (int64_t)row * D);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int col = lane + v * 32;
+        zv[r][v] = ((r0 + r) < count && col < nvec) ? ld_stream(zr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if ((r0 + r) >= count) break;
+      if (codes[r] != cur) {
+        if (cur >= 0) flush_bucket<VPL, true>(acc, cur, p0, p1, 0.f, offsets, total, K, centroids, D, lane);
+        cur = codes[r];
+      }
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        acc[v].x += zv[r][v].x; acc[v].y += zv[r][v].y; acc[v].z += zv[r][v].z; acc[v].w += zv[r][v].w;
+      }
+    }
+  }
+  if (cur >= 0) flush_bucket<VPL, true>(acc, cur, p0, p1, 0.f, offsets, total, K, centroids, D, lane);
+}
+
+// clusters without members keep their previous position (scipy kmeans2, missing='warn')
+__global__ void __launch_bounds__(256) keep_empty_kernel(const int32_t* __restrict__ hist, const float* __restrict__ old_c,
+                                                         int64_t K, int D, float* __restrict__ new_c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= K || hist[k] != 0) return;
+  for (int j = lane; j < D; j += 32) new_c[k * D + j] = old_c[k * D + j];
+}
+
+__global__ void __launch_bounds__(256) histogram_kernel(const int64_t* __restrict__ idx, int64_t N, int64_t K,
+                                                        int64_t k_offset, int32_t* __restrict__ hist) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int64_t code = -1;
+  if (i < N) {
+    code = idx[i] - k_offset;
+    if (code < 0 || code >= K) code = -1;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, code);
+  if (code >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(hist + code, __popc(peers));
+}
+
+int launch_histogram(const int64_t* idx, int64_t N, int64_t K, int64_t k_offset, int32_t* hist, cudaStream_t st) {
+  KVQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int32_t), st));
+  if (N <= 0) return KVQ_OK;
+  histogram_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(idx, N, K, k_offset, hist);
+  KVQ_LAUNCH_CHECK();
+  return KVQ_OK;
 }
 
 // dz only (no codebook gradient wanted): natural order, no bucketing.
@@ -376,6 +460,43 @@ int launch_backward(const float* z, const float* E, const int64_t* idx, const in
     break;
   switch (vpl) { KVQ_SEG(1) KVQ_SEG(2) KVQ_SEG(3) KVQ_SEG(4) KVQ_SEG(5) KVQ_SEG(6) KVQ_SEG(7) KVQ_SEG(8) }
 #undef KVQ_SEG
+  KVQ_LAUNCH_CHECK();
+  return KVQ_OK;
+}
+
+int launch_kmeans_update(const float* z, const int64_t* idx, const int32_t* hist, int64_t N, int D, int64_t K,
+                         const float* old_c, float* new_c, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int vpl = (D / 4 + 31) / 32;
+  KVQ_REQUIRE(vpl >= 1 && vpl <= 8, KVQ_ERR_SHAPE, "kvq_kmeans_update: D=%d not supported (max 1024)", D);
+  KVQ_REQUIRE(ws_bytes >= backward_workspace_bytes(N, K), KVQ_ERR_WORKSPACE, "kvq_kmeans_update: workspace %zu < %zu bytes",
+              ws_bytes, backward_workspace_bytes(N, K));
+  KVQ_REQUIRE(N >= 1 && N <= 0x7fffffffll, KVQ_ERR_SHAPE, "kvq_kmeans_update: bad N=%lld", (long long)N);
+  char* p = static_cast<char*>(ws);
+  int32_t* offsets = reinterpret_cast<int32_t*>(p); p += align_up((size_t)K * 4, 256);
+  int32_t* cursor = reinterpret_cast<int32_t*>(p);  p += align_up((size_t)K * 4, 256);
+  const int nb = scan_blocks(K);
+  int32_t* block_sums = reinterpret_cast<int32_t*>(p); p += align_up((size_t)(nb + 1) * 4, 256);
+  int32_t* total = reinterpret_cast<int32_t*>(p); p += 256;
+  int2* slots = reinterpret_cast<int2*>(p);
+  KVQ_CUDA(cudaMemsetAsync(new_c, 0, (size_t)K * D * sizeof(float), st));
+  scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(hist, K, block_sums);
+  KVQ_LAUNCH_CHECK();
+  scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
+  KVQ_LAUNCH_CHECK();
+  scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(hist, K, block_sums, offsets, cursor);
+  KVQ_LAUNCH_CHECK();
+  bucket_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(idx, N, K, 0, cursor, slots);
+  KVQ_LAUNCH_CHECK();
+  const int wpb = 8;
+  const unsigned blocks = (unsigned)(((N + 31) / 32 + wpb - 1) / wpb);
+#define KVQ_MEAN(V)                                                                                     \
+  case V:                                                                                               \
+    segment_mean_kernel<V><<<blocks, wpb * 32, 0, st>>>(z, slots, offsets, total, D, K, new_c);           \
+    break;
+  switch (vpl) { KVQ_MEAN(1) KVQ_MEAN(2) KVQ_MEAN(3) KVQ_MEAN(4) KVQ_MEAN(5) KVQ_MEAN(6) KVQ_MEAN(7) KVQ_MEAN(8) }
+#undef KVQ_MEAN
+  KVQ_LAUNCH_CHECK();
+  keep_empty_kernel<<<(unsigned)((K + wpb - 1) / wpb), wpb * 32, 0, st>>>(hist, old_c, K, D, new_c);
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }

@@ -1,0 +1,72 @@
+"""Data-driven codebook initialisation on the device.
+
+Replaces the offline SciPy step of models/shelgon3/vq_codebook_init_weights.py:79-101
+(`scipy.cluster.vq.kmeans2(data, N_E, minit='points')`): Lloyd iterations built from the layer's own kernels --
+fused distance + argmin for the assignment, the bucketed segment pass for the centroid means.  Same call shape
+and return value as kmeans2 for the options the reference uses.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import torch
+
+from . import _lib
+from . import functional as F
+from ._lib import check
+
+
+def kmeans2(data: torch.Tensor, k: Union[int, torch.Tensor], iter: int = 10, minit: str = "points",
+            seed: Optional[int] = None, search: str = "fp32") -> Tuple[torch.Tensor, torch.Tensor]:
+    """k-means with `iter` Lloyd iterations.  data: (N, D) fp32 CUDA tensor.
+
+    minit='points': k distinct random observations as initial centroids (seeded);  minit='matrix': `k` is the
+    (K, D) initial centroid matrix.  Clusters that lose all members keep their previous position.
+    Returns (centroids (K, D) fp32, labels (N,) int64 from the last assignment) like scipy's kmeans2.
+    `search="fp32"` (default) assigns with exact fp32 distances as SciPy does; "tf32" uses the tensor-core search."""
+    F._req(data, "data", torch.float32)
+    if data.dim() != 2:
+        raise ValueError("Input of rank > 2 is not supported.")
+    N, D = data.shape
+    if N < 1:
+        raise ValueError("Empty input is not supported.")
+    if minit == "matrix" or isinstance(k, torch.Tensor):
+        cent = F._req(k.to(data.device).contiguous(), "k", torch.float32).clone()
+        if cent.dim() != 2 or cent.shape[1] != D:
+            raise ValueError("k array doesn't match data dimension")
+    elif minit == "points":
+        K = int(k)
+        if K < 1:
+            raise ValueError(f"Cannot ask kmeans2 for {K} clusters (k was {k})")
+        gen = torch.Generator(device=data.device)
+        gen.manual_seed(torch.initial_seed() if seed is None else int(seed))
+        pick = torch.randperm(N, device=data.device, generator=gen)[:K]
+        cent = data[pick].clone()
+        if cent.shape[0] < K:
+            raise ValueError("more clusters than observations")
+    else:
+        raise ValueError(f"Unknown init method {minit!r}")
+    K = cent.shape[0]
+    lib = _lib.load()
+    ws = F.workspace(N, D, K, data.device)
+    hist = torch.empty(K, dtype=torch.int32, device=data.device)
+    nxt = torch.empty_like(cent)
+    labels = torch.zeros(N, dtype=torch.int64, device=data.device)
+    stream = torch.cuda.current_stream().cuda_stream
+    with torch.cuda.device(data.device):
+        for _ in range(iter):
+            labels, _ = F.search(data, cent, mode=search, ws=ws)
+            check(lib.kvq_histogram(labels.data_ptr(), N, K, 0, hist.data_ptr(), stream), "kvq_histogram")
+            check(lib.kvq_kmeans_update(data.data_ptr(), labels.data_ptr(), hist.data_ptr(), N, D, K, cent.data_ptr(),
+                                        nxt.data_ptr(), ws.data_ptr(), ws.numel(), stream), "kvq_kmeans_update")
+            cent, nxt = nxt, cent
+    return cent, labels
+
+
+def codebook_init_values(latents: torch.Tensor, n_e: int, iter: int = 10, seed: Optional[int] = None,
+                         search: str = "fp32") -> dict:
+    """The dictionary the reference script saves (vq_codebook_init_weights.py:93-100, minus the model-name strings):
+    {"codebook_init_values": Tensor[n_e, e_dim]} from (B, S, e_dim) or (N, e_dim) encoder outputs."""
+    flat = latents.reshape(-1, latents.shape[-1]).contiguous()
+    cent, _ = kmeans2(flat, n_e, iter=iter, minit="points", seed=seed, search=search)
+    return {"codebook_init_values": cent.cpu()}

@@ -93,3 +93,33 @@ def test_host_end_to_end_matches_device_path():
     assert abs(float(out2["perplexity"]) - float(out["perplexity"])) <= 1e-6 * float(out["perplexity"])
     assert (out2["dE"] - out["dE"]).abs().max() <= 1e-6 * out["dE"].abs().max()
     F._lib.load().kvq_host_release()
+
+
+def test_kmeans2_matches_scipy_given_the_same_initial_centroids():
+    """Device Lloyd iterations vs scipy.cluster.vq.kmeans2 (the call of vq_codebook_init_weights.py:85)."""
+    from scipy.cluster.vq import kmeans2 as sp_kmeans2
+    k = _kvq()
+    gen = torch.Generator().manual_seed(3)
+    centers = torch.randn(12, 64, generator=gen) * 4
+    data = (centers[torch.randint(0, 12, (6000,), generator=gen)] + torch.randn(6000, 64, generator=gen)).contiguous()
+    init = data[torch.randperm(6000, generator=gen)[:16]].clone()           # 16 > 12 true clusters
+    init[15] = 100.0                                                         # a centroid that never gets members
+    ref_c, ref_l = sp_kmeans2(data.numpy(), init.numpy().copy(), iter=10, minit="matrix", missing="warn")
+    c, l = k.kmeans2(data.to(DEV), init.to(DEV), iter=10, minit="matrix", search="fp32")
+    assert torch.equal(l.cpu(), torch.from_numpy(ref_l).long())
+    assert torch.allclose(c.cpu(), torch.from_numpy(ref_c), rtol=1e-5, atol=1e-5)
+    assert torch.equal(c[15].cpu(), init[15])                                # empty cluster keeps its position
+    # minit='points': centroids are data points after 0 iterations, K distinct rows, reproducible per seed
+    c0, _ = k.kmeans2(data.to(DEV), 9, iter=0, minit="points", seed=5)
+    assert c0.shape == (9, 64) and all(bool((data == r).all(1).any()) for r in c0.cpu())
+    c1, l1 = k.kmeans2(data.to(DEV), 9, iter=10, minit="points", seed=5)
+    c2, l2 = k.kmeans2(data.to(DEV), 9, iter=10, minit="points", seed=5)
+    assert torch.equal(l1, l2) and torch.allclose(c1, c2, rtol=1e-6, atol=1e-6)
+    # within-cluster distortion does not increase over iterations (Lloyd property), large shape, tf32 search
+    big = torch.randn(1 << 16, 256, device=DEV)
+    cb3, lb3 = k.kmeans2(big, 512, iter=3, seed=1, search="tf32")
+    cb8, lb8 = k.kmeans2(big, 512, iter=8, seed=1, search="tf32")
+    d3 = float(((big - cb3[lb3]) ** 2).sum()); d8 = float(((big - cb8[lb8]) ** 2).sum())
+    assert d8 <= d3 * (1 + 1e-4)
+    out = k.codebook_init_values(big.view(1024, 64, 256), 9, iter=2, seed=0)
+    assert out["codebook_init_values"].shape == (9, 256) and not out["codebook_init_values"].is_cuda
