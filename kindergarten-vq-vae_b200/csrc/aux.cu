@@ -236,11 +236,12 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
     KVQ_TRYC(cudaMemcpyAsync(idx_h + r0, hp.idx + r0, (size_t)rows * 8, cudaMemcpyDeviceToHost, hp.s_out));
   }
   if (status == KVQ_OK) {
+    // loss / perplexity first: the internal sq_sum lives in the workspace the bucketed backward reuses
+    if (!sharded) KVQ_TRY(launch_finalize(sq_sum, hist, N, D, K, beta, hp.scal, hp.scal + 1, hp.s_cmp));
     // codebook gradient over all local rows (bucketed by code); dz was already produced per chunk
     KVQ_TRY(launch_backward(hp.z, hp.E, hp.idx, hist, nullptr, hp.scal + 2, N, D, K, 0, beta, n_global, nullptr, dE, hp.ws,
                             hp.cap_ws, hp.s_cmp));
     if (!sharded) {
-      KVQ_TRY(launch_finalize(sq_sum, hist, N, D, K, beta, hp.scal, hp.scal + 1, hp.s_cmp));
       KVQ_TRYC(cudaMemcpyAsync(loss_h, hp.scal, 4, cudaMemcpyDeviceToHost, hp.s_cmp));
       KVQ_TRYC(cudaMemcpyAsync(perp_h, hp.scal + 1, 4, cudaMemcpyDeviceToHost, hp.s_cmp));
       KVQ_TRYC(cudaMemcpyAsync(dE_h, dE, (size_t)K * D * 4, cudaMemcpyDeviceToHost, hp.s_cmp));

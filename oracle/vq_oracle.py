@@ -267,3 +267,31 @@ def literal_step_cpu(z: torch.Tensor, E: torch.Tensor, beta: float, g_zq: torch.
     perplexity = torch.exp(-torch.sum(usage * torch.log(usage + 1e-10)))
     torch.autograd.backward([loss, out], [torch.ones(()), g_zq])
     return loss.detach(), perplexity.detach(), nearest.view(*z.shape[:-1], 1), zr.grad, W.grad
+
+
+class LiteralVectorQuantizer(torch.nn.Module):
+    """The reference layer restated as a module (same ops as `literal_step_cpu`, any device): the A/B partner of
+    the kvq module in tools/shelgon_step.py on machines where /root/reference is not mounted.  TEST INFRASTRUCTURE."""
+
+    def __init__(self, n_e, e_dim, beta, vq_codebook_init_values=None):
+        super().__init__()
+        self.n_e, self.e_dim, self.beta = n_e, e_dim, beta
+        self.embedding = torch.nn.Embedding(n_e, e_dim)
+        if vq_codebook_init_values is not None:
+            self.embedding.weight.data.copy_(vq_codebook_init_values)
+        else:
+            self.embedding.weight.data.uniform_(-1.0 / n_e, 1.0 / n_e)
+
+    def forward(self, z, device):
+        W = self.embedding.weight
+        flat = z.view(-1, self.e_dim)
+        d = torch.sum(flat ** 2, dim=1, keepdim=True) + torch.sum(W ** 2, dim=1) - 2 * torch.matmul(flat, W.t())
+        nearest = torch.argmin(d, dim=1).unsqueeze(1)
+        hot = torch.zeros(nearest.shape[0], self.n_e).to(device)
+        hot.scatter_(1, nearest, 1)
+        q = torch.matmul(hot, W).view(z.shape)
+        loss = torch.mean((q.detach() - z) ** 2) + self.beta * torch.mean((q - z.detach()) ** 2)
+        out = z + (q - z).detach()
+        usage = torch.mean(hot, dim=0)
+        perplexity = torch.exp(-torch.sum(usage * torch.log(usage + 1e-10)))
+        return loss, out, perplexity, hot, nearest.reshape(z.shape[0], z.shape[1], 1)
