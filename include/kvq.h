@@ -86,6 +86,24 @@ int kvq_search(const float* z, const float* E, int64_t N, int D, int64_t K, int6
                int64_t* idx, int64_t* keys, int keys_accumulate,
                void* workspace, size_t workspace_bytes, kvq_stream_t stream);
 
+/* Fused search + cross-GPU argmin for a codebook sharded over the GPUs of one NVLink / NVSwitch domain.
+ * `peer_keys` is a HOST array of n_peers DEVICE pointers: the packed-key buffer (N int64, pre-filled with INT64_MAX)
+ * of every rank, this rank's own buffer included, all mapped into this process (CUDA IPC / symmetric memory).  The
+ * search kernel's epilogue MIN-combines each row's (score, index) key straight into every rank's buffer with
+ * system-scope 64-bit atomics over NVLink, tile by tile while the tensor cores keep working -- no separate
+ * collective.  After a cross-rank barrier every buffer holds the global argmin (kvq_keys_to_idx). */
+int kvq_search_peers(const float* z, const float* E, int64_t N, int D, int64_t K, int64_t k_offset, int mode,
+                     int64_t* const* peer_keys, int n_peers, int my_rank,
+                     void* workspace, size_t workspace_bytes, kvq_stream_t stream);
+
+/* kvq_quantize for a sharded codebook whose shards are all peer-mapped: `shard_ptrs` is a HOST array of n_shards
+ * DEVICE pointers, shard g holding global rows [g*k_per, (g+1)*k_per).  Every latent's winning row is gathered from
+ * its owner's memory (NVLink peer loads); z_q, the squared-residual sum and the histogram over all K_total codes
+ * are complete on every rank without any collective. */
+int kvq_quantize_shards(const float* z, const float* const* shard_ptrs, int n_shards, int64_t k_per,
+                        const int64_t* idx, int64_t N, int D, int64_t K_total, float* z_q, double* sq_sum,
+                        int32_t* hist, kvq_stream_t stream);
+
 /* Host helper: the packed key kvq_search emits for (score, index).  Signed int64 comparison of two keys orders
  * them by score first (IEEE order, -0 == +0) and by index second. */
 int64_t kvq_pack_key(float score, uint32_t index);

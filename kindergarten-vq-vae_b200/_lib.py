@@ -30,6 +30,8 @@ SIGNATURES = {
     "kvq_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64]),
     "kvq_code_norms": (c_int, [_P, c_int64, c_int, _P, c_int64, _P]),
     "kvq_search": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int, _P, _P, c_int, _P, c_size_t, _P]),
+    "kvq_search_peers": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int64, c_int, _P, c_int, c_int, _P, c_size_t, _P]),
+    "kvq_quantize_shards": (c_int, [_P, _P, c_int, c_int64, _P, c_int64, c_int, c_int64, _P, _P, _P, _P]),
     "kvq_pack_key": (c_int64, [c_float, ctypes.c_uint32]),
     "kvq_keys_to_idx": (c_int, [_P, c_int64, _P, _P]),
     "kvq_quantize": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, c_int64, c_int, _P, _P, _P, _P]),

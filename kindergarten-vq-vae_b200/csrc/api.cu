@@ -182,6 +182,44 @@ int kvq_search(const float* z, const float* E, int64_t N, int D, int64_t K, int6
   return launch_search_fp32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
 }
 
+int kvq_search_peers(const float* z, const float* E, int64_t N, int D, int64_t K, int64_t k_offset, int mode,
+                     int64_t* const* peer_keys, int n_peers, int my_rank, void* ws, size_t ws_bytes, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  rc = check_shape("kvq_search_peers", N, D, K); if (rc) return rc;
+  KVQ_REQUIRE(z && E && ws && peer_keys, KVQ_ERR_ARG, "kvq_search_peers: null pointer");
+  KVQ_REQUIRE(n_peers >= 1 && n_peers <= MAX_PEERS && my_rank >= 0 && my_rank < n_peers, KVQ_ERR_ARG,
+              "kvq_search_peers: n_peers must be 1..%d and my_rank inside it", MAX_PEERS);
+  KVQ_REQUIRE(k_offset >= 0 && k_offset + K <= 0xffffffffll, KVQ_ERR_SHAPE, "kvq_search_peers: k_offset + K exceeds 2^32");
+  KVQ_REQUIRE(((uintptr_t)ws & 255) == 0, KVQ_ERR_WORKSPACE, "kvq_search_peers: workspace must be 256-byte aligned");
+  FwdWs w = carve_forward(ws, N, K);
+  KVQ_REQUIRE(ws_bytes >= w.bytes, KVQ_ERR_WORKSPACE, "kvq_search_peers: workspace %zu < %zu bytes", ws_bytes, w.bytes);
+  PeerKeys pk;
+  for (int g = 0; g < MAX_PEERS; ++g) pk.p[g] = g < n_peers ? reinterpret_cast<long long*>(peer_keys[g]) : nullptr;
+  for (int g = 0; g < n_peers; ++g) KVQ_REQUIRE(pk.p[g], KVQ_ERR_ARG, "kvq_search_peers: peer %d has a null key buffer", g);
+  pk.n = n_peers;
+  pk.first = (my_rank + 1) % n_peers;
+  int m; rc = resolve_mode(mode, N, D, K, &m); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); if (rc) return rc;
+  if (m == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, w.e2, N, D, K, k_offset, nullptr, nullptr, 0, st, &pk);
+  return launch_search_fp32(z, E, w.e2, N, D, K, k_offset, nullptr, nullptr, 0, st, &pk);
+}
+
+int kvq_quantize_shards(const float* z, const float* const* shard_ptrs, int n_shards, int64_t k_per, const int64_t* idx,
+                        int64_t N, int D, int64_t K_total, float* z_q, double* sq_sum, int32_t* hist, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  rc = check_shape("kvq_quantize_shards", N, D, K_total); if (rc) return rc;
+  KVQ_REQUIRE(z && shard_ptrs && idx && z_q && sq_sum && hist, KVQ_ERR_ARG, "kvq_quantize_shards: null pointer");
+  KVQ_REQUIRE(n_shards >= 1 && n_shards <= MAX_PEERS && k_per >= 1 && k_per * n_shards >= K_total, KVQ_ERR_ARG,
+              "kvq_quantize_shards: bad shard table");
+  ShardPtrs sp;
+  for (int g = 0; g < MAX_PEERS; ++g) sp.p[g] = g < n_shards ? shard_ptrs[g] : nullptr;
+  for (int g = 0; g < n_shards; ++g) KVQ_REQUIRE(sp.p[g], KVQ_ERR_ARG, "kvq_quantize_shards: shard %d is null", g);
+  sp.n = n_shards;
+  sp.k_per = k_per;
+  return launch_quantize(z, sp.p[0], idx, N, D, K_total, 0, 0, z_q, sq_sum, hist, (cudaStream_t)stream, &sp);
+}
+
 int64_t kvq_pack_key(float score, uint32_t index) { return (int64_t)pack_key(score, index); }
 
 int kvq_keys_to_idx(const int64_t* keys, int64_t N, int64_t* idx, kvq_stream_t stream) {

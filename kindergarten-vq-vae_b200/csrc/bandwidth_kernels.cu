@@ -75,7 +75,8 @@ template <int VPL>
 __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                        const int64_t* __restrict__ idx, int64_t N, int D, int64_t K,
                                                        int64_t k_offset, int zero_skipped, float* __restrict__ z_q,
-                                                       double* __restrict__ sq_sum, int32_t* __restrict__ hist) {
+                                                       double* __restrict__ sq_sum, int32_t* __restrict__ hist,
+                                                       const ShardPtrs shards) {
   constexpr int R = (VPL <= 2) ? 4 : ((VPL <= 4) ? 2 : 1);  // rows in flight, bounded by registers
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -104,7 +105,10 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
         c[r] = __shfl_sync(0xffffffffu, code, (r0 + r) & 31);
         const bool live = (r0 + r) < rows_here;
         const float4* zr = reinterpret_cast<const float4*>(z + (row0 + r0 + r) * (int64_t)D);
-        const float4* er = reinterpret_cast<const float4*>(E + (c[r] < 0 ? 0 : c[r]) * (int64_t)D);
+        const int64_t cc = c[r] < 0 ? 0 : c[r];
+        // sharded codebook: the winning row is read from its owner's HBM through the NVLink peer mapping
+        const float* erow = shards.n ? shards.p[cc / shards.k_per] + (cc % shards.k_per) * (int64_t)D : E + cc * (int64_t)D;
+        const float4* er = reinterpret_cast<const float4*>(erow);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
           const int col = lane + v * 32;
@@ -152,15 +156,18 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
 }
 
 int launch_quantize(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int64_t K,
-                    int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st) {
+                    int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st,
+                    const ShardPtrs* shards) {
   if (N <= 0) return KVQ_OK;
+  ShardPtrs sp;
+  if (shards) sp = *shards; else { sp.n = 0; sp.k_per = 1; }
   const int wpb = 8;
   const int64_t warps = (N + 31) / 32;
   const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
   const int vpl = (D / 4 + 31) / 32;
 #define KVQ_Q(V)                                                                                            \
   case V:                                                                                                   \
-    quantize_kernel<V><<<blocks, wpb * 32, 0, st>>>(z, E, idx, N, D, K, k_offset, zero_skipped, z_q, sq_sum, hist); \
+    quantize_kernel<V><<<blocks, wpb * 32, 0, st>>>(z, E, idx, N, D, K, k_offset, zero_skipped, z_q, sq_sum, hist, sp); \
     break;
   switch (vpl) {
     KVQ_Q(1) KVQ_Q(2) KVQ_Q(3) KVQ_Q(4) KVQ_Q(5) KVQ_Q(6) KVQ_Q(7) KVQ_Q(8)

@@ -93,17 +93,33 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- multi-GPU peer tables (NVLink peer pointers, passed to kernels by value) --------------------------------
+constexpr int MAX_PEERS = 8;
+struct PeerKeys {            // packed-key buffers of every rank of the codebook-sharded group (incl. this rank)
+  long long* p[MAX_PEERS];
+  int n;                     // 0 = no peers (single-GPU behaviour)
+  int first;                 // rank-dependent starting peer, so ranks do not all hit the same GPU at once
+};
+struct ShardPtrs {           // codebook shards of every rank: global code c lives at p[c / k_per] + (c % k_per) * D
+  const float* p[MAX_PEERS];
+  int n;
+  int64_t k_per;
+};
+
 // ---- kernels' host launchers (one per translation unit) --------------------------------------------
 int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st);
 int launch_search_fp32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
-                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st);
+                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st,
+                       const PeerKeys* peers = nullptr);
 int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
-                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st);
+                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st,
+                       const PeerKeys* peers = nullptr);
 bool tf32_shape_ok(int64_t N, int D, int64_t K);
 int launch_fill_keys(long long* keys, int64_t N, cudaStream_t st);
 int launch_keys_to_idx(const long long* keys, int64_t N, int64_t* idx, cudaStream_t st);
 int launch_quantize(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int64_t K,
-                    int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st);
+                    int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st,
+                    const ShardPtrs* shards = nullptr);
 int launch_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, int D, int64_t K, float beta,
                     float* loss, float* perplexity, cudaStream_t st);
 int launch_backward(const float* z, const float* E, const int64_t* idx, const int32_t* hist, const float* g_zq,

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(F_THREADS) search_fp32_kernel(const float* __r
                                                                 const float* __restrict__ e2, int64_t N, int D,
                                                                 int64_t K, int64_t k_offset, int tiles_per_split,
                                                                 int64_t* __restrict__ idx, long long* __restrict__ keys,
-                                                                int use_atomic) {
+                                                                int use_atomic, const PeerKeys peers) {
   __shared__ __align__(16) float As[F_BK][F_BM + 4];
   __shared__ __align__(16) float Bs[F_BK][F_BN + 4];
 
@@ -99,7 +99,13 @@ __global__ void __launch_bounds__(F_THREADS) search_fp32_kernel(const float* __r
     if (tx == 0) {
       const int64_t row = m0 + ((i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4)));
       if (row < N) {
-        if (use_atomic) {
+        if (peers.n > 0) {
+          for (int g = 0; g < peers.n; ++g) {   // fused cross-GPU argmin over NVLink peer memory
+            int t = peers.first + g;
+            if (t >= peers.n) t -= peers.n;
+            atomicMin_system(peers.p[t] + row, key);
+          }
+        } else if (use_atomic) {
           atomicMin(keys + row, key);
         } else {
           if (keys) keys[row] = key;
@@ -111,8 +117,11 @@ __global__ void __launch_bounds__(F_THREADS) search_fp32_kernel(const float* __r
 }
 
 int launch_search_fp32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
-                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st) {
+                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st,
+                       const PeerKeys* peers) {
   if (N <= 0) return KVQ_OK;
+  PeerKeys pk;
+  if (peers) pk = *peers; else pk.n = 0;
   const int64_t m_tiles = (N + F_BM - 1) / F_BM;
   const int n_tiles = (int)((K + F_BN - 1) / F_BN);
   // split the code range when there are too few row tiles to fill the GPU (2 CTAs/SM target)
@@ -123,18 +132,18 @@ int launch_search_fp32(const float* z, const float* E, const float* e2, int64_t 
   const int tiles_per_split = (n_tiles + split - 1) / split;
   split = (n_tiles + tiles_per_split - 1) / tiles_per_split;
   const int use_atomic = (split > 1 || keys_accumulate) ? 1 : 0;
-  KVQ_REQUIRE(!use_atomic || keys, KVQ_ERR_ARG, "kvq_search(fp32): split/accumulate search needs a keys buffer");
-  if (use_atomic && !keys_accumulate) {
+  KVQ_REQUIRE(pk.n > 0 || !use_atomic || keys, KVQ_ERR_ARG, "kvq_search(fp32): split/accumulate search needs a keys buffer");
+  if (pk.n == 0 && use_atomic && !keys_accumulate) {
     int rc = launch_fill_keys(keys, N, st);
     if (rc) return rc;
   }
   dim3 grid((unsigned)m_tiles, (unsigned)split);
   {
     ProfScope ps(KVQ_PROF_SEARCH, st);
-    search_fp32_kernel<<<grid, F_THREADS, 0, st>>>(z, E, e2, N, D, K, k_offset, tiles_per_split, idx, keys, use_atomic);
+    search_fp32_kernel<<<grid, F_THREADS, 0, st>>>(z, E, e2, N, D, K, k_offset, tiles_per_split, idx, keys, use_atomic, pk);
     KVQ_LAUNCH_CHECK();
   }
-  if (use_atomic && idx) return launch_keys_to_idx(keys, N, idx, st);
+  if (pk.n == 0 && use_atomic && idx) return launch_keys_to_idx(keys, N, idx, st);
   return KVQ_OK;
 }
 

@@ -70,6 +70,7 @@ struct Params {
   const float* e2;      // padded to n_tiles*256 with +inf
   int64_t* idx;
   long long* keys;
+  PeerKeys peers;       // n > 0: MIN-combine the packed keys straight into every rank's buffer over NVLink
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -467,7 +468,14 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
         if (row < p.N) {
           const uint32_t gi = (uint32_t)(bi + p.k_offset);
           const long long key = pack_key(bv, gi);
-          if (p.use_atomic) {
+          if (p.peers.n > 0) {
+            // fused cross-GPU argmin: system-scope 64-bit atomicMin on peer-mapped memory (NVLink), staggered by rank
+            for (int g = 0; g < p.peers.n; ++g) {
+              int t = p.peers.first + g;
+              if (t >= p.peers.n) t -= p.peers.n;
+              atomicMin_system(p.peers.p[t] + row, key);
+            }
+          } else if (p.use_atomic) {
             atomicMin(p.keys + row, key);
           } else {
             if (p.keys) p.keys[row] = key;
@@ -533,7 +541,7 @@ static int env_int(const char* name, int dflt) {
 
 template <int CG>
 static int launch_cg(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t k_offset,
-                     int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st) {
+                     int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st, const PeerKeys* peers) {
   constexpr int B_STAGE_BYTES = (BLOCK_N / CG) * BLOCK_K * 4;
   Params p;
   p.N = N; p.K = K; p.k_offset = k_offset; p.D = D;
@@ -558,7 +566,9 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   p.stages = stages;
   p.use_atomic = (p.ksplit > 1 || keys_accumulate) ? 1 : 0;
   p.e2 = e2; p.idx = idx; p.keys = keys;
-  KVQ_REQUIRE(!p.use_atomic || keys, KVQ_ERR_ARG, "kvq_search(tf32): split/accumulate search needs a keys buffer");
+  if (peers) p.peers = *peers; else p.peers.n = 0;
+  KVQ_REQUIRE(p.peers.n > 0 || !p.use_atomic || keys, KVQ_ERR_ARG,
+              "kvq_search(tf32): split/accumulate search needs a keys buffer");
   const size_t smem = 1024 + SMEM_CTRL_BYTES + (size_t)a_bytes + (size_t)stages * stage_bytes;
 
   static const bool round_tf32 = env_int("KVQ_TMA_ROUND_TF32", 1) != 0;
@@ -568,7 +578,7 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   rc = make_map(&me, E, K, D, BLOCK_N / CG, round_tf32);
   if (rc) return rc;
 
-  if (p.use_atomic && !keys_accumulate) {
+  if (p.peers.n == 0 && p.use_atomic && !keys_accumulate) {
     rc = launch_fill_keys(keys, N, st);
     if (rc) return rc;
   }
@@ -591,7 +601,7 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
     count_launch();
     KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG>, mz, me, p));
   }
-  if (p.use_atomic && idx && !keys_accumulate) return launch_keys_to_idx(keys, N, idx, st);
+  if (p.peers.n == 0 && p.use_atomic && idx && !keys_accumulate) return launch_keys_to_idx(keys, N, idx, st);
   return KVQ_OK;
 }
 
@@ -602,15 +612,16 @@ bool tf32_shape_ok(int64_t N, int D, int64_t K) {
 }
 
 int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
-                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st) {
+                       int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st,
+                       const PeerKeys* peers) {
   if (N <= 0) return KVQ_OK;
   KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (got N=%lld D=%d K=%lld)",
               (long long)N, D, (long long)K);
   KVQ_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)E & 15) == 0, KVQ_ERR_ARG,
               "tf32 search needs 16-byte aligned z and E (TMA)");
   static const int cta_group = t5::env_int("KVQ_TF32_CTA_GROUP", 2);
-  if (cta_group == 1) return t5::launch_cg<1>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st);
-  return t5::launch_cg<2>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st);
+  if (cta_group == 1) return t5::launch_cg<1>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers);
+  return t5::launch_cg<2>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers);
 }
 
 }  // namespace kvq

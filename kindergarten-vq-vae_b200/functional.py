@@ -247,3 +247,35 @@ def forward_backward_host_sharded(z: torch.Tensor, E: torch.Tensor, g_zq: torch.
     torch.cuda.synchronize()
     out["loss"], out["perplexity"] = out["scal"][0], out["scal"][1]
     return out
+
+
+def search_peers(z: torch.Tensor, E: torch.Tensor, peer_key_ptrs, my_rank: int, *, mode: str = "auto", k_offset: int = 0,
+                 ws: Optional[torch.Tensor] = None) -> None:
+    """Fused search + cross-GPU argmin: MIN-combines packed keys into every rank's (peer-mapped) key buffer."""
+    import ctypes
+    _req(z, "z", torch.float32); _req(E, "E", torch.float32)
+    N, D = z.shape
+    K = E.shape[0]
+    if ws is None:
+        ws = workspace(N, D, K, z.device)
+    arr = (ctypes.c_void_p * len(peer_key_ptrs))(*[int(p) for p in peer_key_ptrs])
+    with torch.cuda.device(z.device):
+        check(_lib.load().kvq_search_peers(z.data_ptr(), E.data_ptr(), N, D, K, k_offset, SEARCH_MODES[mode], arr,
+                                           len(peer_key_ptrs), my_rank, ws.data_ptr(), ws.numel(), _stream()),
+              "kvq_search_peers")
+
+
+def quantize_shards(z: torch.Tensor, shard_ptrs, k_per: int, idx: torch.Tensor, K_total: int):
+    """Gather + straight-through + loss sum + full histogram with codebook rows read from peer-mapped shards."""
+    import ctypes
+    _req(z, "z", torch.float32); _req(idx, "idx", torch.int64)
+    N, D = z.shape
+    z_q = torch.empty_like(z)
+    sq_sum = torch.zeros(1, dtype=torch.float64, device=z.device)
+    hist = torch.zeros(K_total, dtype=torch.int32, device=z.device)
+    arr = (ctypes.c_void_p * len(shard_ptrs))(*[int(p) for p in shard_ptrs])
+    with torch.cuda.device(z.device):
+        check(_lib.load().kvq_quantize_shards(z.data_ptr(), arr, len(shard_ptrs), k_per, idx.data_ptr(), N, D, K_total,
+                                              z_q.data_ptr(), sq_sum.data_ptr(), hist.data_ptr(), _stream()),
+              "kvq_quantize_shards")
+    return z_q, sq_sum, hist

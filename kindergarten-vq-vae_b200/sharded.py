@@ -168,18 +168,93 @@ class _CodebookShardedFn(torch.autograd.Function):
         return dz, dE, None, None, None, None, None, None
 
 
+class _PeerMemory:
+    """NVLink-peer-mapped buffers of the codebook-sharded layer (torch symmetric memory = CUDA VMM + IPC handles):
+    one packed-key buffer per rank (N int64) and one codebook-shard mirror per rank (k_per x D fp32)."""
+
+    def __init__(self, group, k_per: int, D: int, device):
+        import torch.distributed._symmetric_memory as symm
+        self.symm = symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.device = device
+        self.mirror = symm.empty(k_per, D, dtype=torch.float32, device=device)
+        self.mirror_h = symm.rendezvous(self.mirror, self.group)
+        self.keys = None
+        self.keys_h = None
+
+    def keys_for(self, N: int):
+        if self.keys is None or self.keys.numel() != N:
+            self.keys = self.symm.empty(N, dtype=torch.int64, device=self.device)
+            self.keys_h = self.symm.rendezvous(self.keys, self.group)
+        return self.keys, self.keys_h
+
+
+class _CodebookShardedFusedFn(torch.autograd.Function):
+    """Codebook-sharded forward with NO collective library call: the search kernel MIN-combines packed keys into every
+    rank's key buffer over NVLink (system-scope atomics on peer memory), the gather kernel reads winning rows from the
+    owner's shard through the peer mapping; three device-side barriers order the phases."""
+
+    @staticmethod
+    def forward(ctx, z, E_local, beta, mode, peer: _PeerMemory, rank, world, k_offset, k_total):
+        N, D = z.shape
+        k_per = E_local.shape[0]
+        keys, kh = peer.keys_for(N)
+        keys.fill_(torch.iinfo(torch.int64).max)
+        peer.mirror.copy_(E_local.detach())
+        kh.barrier(channel=0)                       # every rank's key buffer is initialised, every mirror refreshed
+        _cuda_backend.search_peers(z, E_local, kh.buffer_ptrs, rank, mode=mode, k_offset=k_offset)
+        kh.barrier(channel=1)                       # all remote atomics have landed: keys hold the global argmin
+        idx = _cuda_backend.keys_to_idx(keys)
+        z_q, sq_sum, hist_all = _cuda_backend.quantize_shards(z, peer.mirror_h.buffer_ptrs, k_per, idx, k_per * world)
+        kh.barrier(channel=0)                       # peers are done reading this rank's mirror
+        hist = hist_all[:k_total].contiguous()
+        loss, perplexity = _cuda_backend.finalize(sq_sum, hist, N, D, beta)
+        loss, perplexity = loss.clone(), perplexity.clone()
+        hist_local = hist_all[k_offset:k_offset + k_per].contiguous()
+        ctx.save_for_backward(z, E_local, idx, hist_local, z_q)
+        ctx.beta, ctx.k_offset = beta, k_offset
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(perplexity, idx, hist)
+        return loss, z_q, perplexity, idx, hist
+
+    @staticmethod
+    def backward(ctx, g_loss, g_zq, *_):
+        z, E_local, idx, hist_local, z_q = ctx.saved_tensors
+        need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_zq is not None:
+            g_zq = g_zq.contiguous()
+        none = (None,) * 7
+        if g_loss is None:
+            return ((g_zq if need_dz else None), (torch.zeros_like(E_local) if need_dE else None)) + none
+        g_loss = g_loss.detach().to(torch.float32).contiguous()
+        dz = _cuda_backend.dz_from_zq(z, z_q, g_zq, g_loss, z.shape[0]) if need_dz else None
+        dE = None
+        if need_dE:
+            _, dE = _cuda_backend.vq_backward(z, E_local, idx, hist_local, ctx.beta, g_zq=None, g_loss=g_loss,
+                                              need_dz=False, need_dE=True, k_offset=ctx.k_offset)
+        return (dz, dE) + none
+
+
 class CodebookShardedVectorQuantizer(nn.Module):
     """VectorQuantizer whose codebook rows are sharded over the ranks of `process_group` (latents replicated).
     `embedding` holds only this rank's shard: rows [k_offset, k_offset + k_local) of the global (n_e, e_dim)
     codebook (all shards have ceil(n_e / world) rows; the tail of the last one is padding that can never win)."""
 
     def __init__(self, n_e, e_dim, beta, vq_codebook_init_values: Tensor = None, *, process_group=None,
-                 search: str = "auto", backend=None):
+                 search: str = "auto", backend=None, exchange: str = "nccl"):
+        """exchange="nccl": all-reduce(MIN) of keys + all-reduce(SUM) of z_q partials (works everywhere);
+        exchange="nvlink": fused path -- the kernels do the exchange themselves over NVLink peer memory
+        (needs torch symmetric memory on one NVLink domain, world <= 8)."""
         super().__init__()
         self.n_e, self.e_dim, self.beta = n_e, e_dim, beta
         self.search, self.group = search, process_group
         self.backend = backend if backend is not None else _cuda_backend
+        if exchange not in ("nccl", "nvlink"):
+            raise ValueError("exchange must be 'nccl' or 'nvlink'")
+        self.exchange = exchange
+        self._peer = None
         world, rank = _world(process_group), _rank(process_group)
+        self.world, self.rank = world, rank
         self.k_per = (n_e + world - 1) // world
         self.k_offset = rank * self.k_per
         lo, hi = shard_bounds(n_e, world, rank)
@@ -198,6 +273,13 @@ class CodebookShardedVectorQuantizer(nn.Module):
     def forward(self, z: Tensor, device=None):
         batch_size, seq_len, _ = z.shape
         zf = z.view((-1, self.e_dim))
+        if self.exchange == "nvlink" and self.world > 1:
+            if self._peer is None:
+                self._peer = _PeerMemory(self.group, self.k_per, self.e_dim, z.device)
+            loss, z_q, perplexity, idx, _ = _CodebookShardedFusedFn.apply(
+                zf, self.embedding.weight, float(self.beta), self.search, self._peer, self.rank, self.world,
+                self.k_offset, self.n_e)
+            return loss, z_q.view(z.shape), perplexity, None, idx.reshape((batch_size, seq_len, 1))
         loss, z_q, perplexity, idx, _ = _CodebookShardedFn.apply(zf, self.embedding.weight, float(self.beta),
                                                                   self.search, self.group, self.k_offset, self.n_e,
                                                                   self.backend)

@@ -48,22 +48,28 @@ def main():
             dE = vq.embedding.weight.grad
             assert float((dE - ref.embedding.weight.grad).abs().max()) <= 2e-5 * float(ref.embedding.weight.grad.abs().max())
 
-        # ---- codebook-sharded ----
-        cq = kvq.CodebookShardedVectorQuantizer(K, D, beta, vq_codebook_init_values=E, search=search).to(dev)
-        zc = z.to(dev).requires_grad_(True)
-        l2, q2, p2, _, i2 = cq.forward(zc, dev)
-        (l2 * w + (q2 * gz.to(dev)).sum()).backward()
-        same = (i2 == i0).reshape(-1)
-        frac = float(same.float().mean())
-        assert frac > 0.999, f"codebook-sharded idx agreement {frac}"
-        assert torch.equal(q2.detach().reshape(-1, D)[same], q0.detach().reshape(-1, D)[same])
-        if frac == 1.0:
-            assert abs(float(l2) - float(l0)) <= 1e-5 * float(l0)
-            assert abs(float(p2) - float(p0)) <= 1e-5 * float(p0)
-            assert torch.allclose(zc.grad, zr.grad, rtol=1e-4, atol=1e-6)
-            dE_ref = ref.embedding.weight.grad[cq.k_offset:cq.k_offset + cq.k_valid]
-            dE = cq.embedding.weight.grad[: cq.k_valid]
-            assert float((dE - dE_ref).abs().max()) <= 2e-5 * float(ref.embedding.weight.grad.abs().max())
+        # ---- codebook-sharded: NCCL exchange, then the fused NVLink peer-memory exchange ----
+        for exchange in ("nccl", "nvlink"):
+            cq = kvq.CodebookShardedVectorQuantizer(K, D, beta, vq_codebook_init_values=E, search=search,
+                                                    exchange=exchange).to(dev)
+            for rep in range(2):            # twice: the peer buffers are reused across forwards
+                cq.zero_grad()
+                zc = z.to(dev).requires_grad_(True)
+                l2, q2, p2, _, i2 = cq.forward(zc, dev)
+                (l2 * w + (q2 * gz.to(dev)).sum()).backward()
+            same = (i2 == i0).reshape(-1)
+            frac = float(same.float().mean())
+            assert frac > 0.999, f"codebook-sharded[{exchange}] idx agreement {frac}"
+            assert torch.equal(q2.detach().reshape(-1, D)[same], q0.detach().reshape(-1, D)[same]), exchange
+            if frac == 1.0:
+                assert abs(float(l2) - float(l0)) <= 1e-5 * float(l0), exchange
+                assert abs(float(p2) - float(p0)) <= 1e-5 * float(p0), exchange
+                assert torch.allclose(zc.grad, zr.grad, rtol=1e-4, atol=1e-6), exchange
+                dE_ref = ref.embedding.weight.grad[cq.k_offset:cq.k_offset + cq.k_valid]
+                dE = cq.embedding.weight.grad[: cq.k_valid]
+                assert float((dE - dE_ref).abs().max()) <= 2e-5 * float(ref.embedding.weight.grad.abs().max()), exchange
+            if rank == 0:
+                print(f"  codebook-sharded exchange={exchange}: idx agreement {frac:.6f}", flush=True)
         if rank == 0:
             print(f"dist check OK: world={world} B={B} S={S} D={D} K={K} {search}", flush=True)
     dist.barrier()

@@ -97,12 +97,12 @@ def multi():
 
     # ---- C4: codebook-sharded, K = 2^20, latents replicated ----
     D, K = 256, 1 << 20
-    for N in (1 << 18, 1 << 20):
+    for N, exchange in ((1 << 18, "nccl"), (1 << 20, "nccl"), (1 << 18, "nvlink"), (1 << 20, "nvlink")):
         g = torch.Generator(device=dev).manual_seed(69)                 # same z on every rank
         z = torch.randn(N, D, device=dev, generator=g); gz = torch.randn(N, D, device=dev, generator=g)
         per = (K + world - 1) // world
         ge = torch.Generator(device=dev).manual_seed(1000 + rank)       # this rank's codebook rows
-        vq = kvq.CodebookShardedVectorQuantizer(K, D, BETA, search="tf32").to(dev)
+        vq = kvq.CodebookShardedVectorQuantizer(K, D, BETA, search="tf32", exchange=exchange).to(dev)
         with torch.no_grad():
             vq.embedding.weight.copy_(torch.randn(per, D, device=dev, generator=ge))
         z3 = z.view(N // 64, 64, D).requires_grad_(True); g3 = gz.view_as(z3)
@@ -116,7 +116,7 @@ def multi():
         prof = profile(lib, step, iters=2)
         if rank == 0:
             ms = float(t)
-            print(json.dumps(dict(config="C4-kshard", gpus=world, N=N, D=D, K=K, ms_fwd_bwd=ms, latents_per_s=N / ms * 1e3,
+            print(json.dumps(dict(config="C4-kshard", exchange=exchange, gpus=world, N=N, D=D, K=K, ms_fwd_bwd=ms, latents_per_s=N / ms * 1e3,
                                   search_ms=prof["search"], search_tflops_per_gpu=2.0 * N * per * D / prof["search"] / 1e9,
                                   aggregate_tflops=2.0 * N * K * D / ms / 1e9)), flush=True)
         del vq, z, gz, z3, g3
