@@ -16,7 +16,8 @@ def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     import kindergarten_vq_vae_b200 as kvq
 
     for (B, S, D, K, search) in [(8 * world, 64, 128, 1000, "fp32"), (16 * world, 64, 256, 4096, "tf32")]:
