@@ -154,6 +154,12 @@ int kvq_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const fl
 /* Code-usage histogram of an index vector: hist[k] = #{i : idx[i] == k_offset + k}  (hist is overwritten). */
 int kvq_histogram(const int64_t* idx, int64_t N, int64_t K, int64_t k_offset, int32_t* hist, kvq_stream_t stream);
 
+/* (token id x code) co-occurrence table for the code-usage analysis
+ * (analyses/unsupervised_vq_disentanglement/unsupervised_vq_disentanglement.py:165-201): table[t*K + c] = number of
+ * positions whose token id is t and whose code index is c (table is V*K int32, overwritten). */
+int kvq_cooccurrence(const int64_t* tokens, const int64_t* codes, int64_t N, int64_t V, int64_t K, int32_t* table,
+                     kvq_stream_t stream);
+
 /* One Lloyd update for the data-driven codebook initialisation (models/shelgon3/vq_codebook_init_weights.py:85,
  * scipy.cluster.vq.kmeans2): new_centroids[k] = mean of the latents with idx == k; clusters without members keep
  * old_centroids[k] (kmeans2's missing='warn' behaviour).  `hist` = kvq_histogram(idx).  Same bucketed pass as the

@@ -41,6 +41,7 @@ SIGNATURES = {
                              _P, c_size_t, _P]),
     "kvq_dz_from_zq": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int64, _P, _P]),
     "kvq_histogram": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),
+    "kvq_cooccurrence": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P]),
     "kvq_kmeans_update": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, _P, _P, _P, c_size_t, _P]),
     "kvq_onehot": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "kvq_seq_acc": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),

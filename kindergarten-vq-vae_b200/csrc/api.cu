@@ -296,6 +296,14 @@ int kvq_histogram(const int64_t* idx, int64_t N, int64_t K, int64_t k_offset, in
   return launch_histogram(idx, N, K, k_offset, hist, (cudaStream_t)stream);
 }
 
+int kvq_cooccurrence(const int64_t* tokens, const int64_t* codes, int64_t N, int64_t V, int64_t K, int32_t* table,
+                     kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  KVQ_REQUIRE(tokens && codes && table && N >= 0 && V >= 1 && K >= 1, KVQ_ERR_ARG, "kvq_cooccurrence: bad arguments");
+  KVQ_REQUIRE(V * K < (1ll << 40), KVQ_ERR_SHAPE, "kvq_cooccurrence: table too large");
+  return launch_cooccurrence(tokens, codes, N, V, K, table, (cudaStream_t)stream);
+}
+
 int kvq_kmeans_update(const float* z, const int64_t* idx, const int32_t* hist, int64_t N, int D, int64_t K,
                       const float* old_centroids, float* new_centroids, void* ws, size_t ws_bytes, kvq_stream_t stream) {
   int rc = check_device(); if (rc) return rc;

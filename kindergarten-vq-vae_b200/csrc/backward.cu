@@ -319,6 +319,30 @@ __global__ void __launch_bounds__(256) histogram_kernel(const int64_t* __restric
   if (code >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(hist + code, __popc(peers));
 }
 
+// (token id x code) co-occurrence counts for the code-usage analysis
+// (analyses/unsupervised_vq_disentanglement/unsupervised_vq_disentanglement.py:165-201 does this with nested Python loops).
+__global__ void __launch_bounds__(256) cooccurrence_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ codes,
+                                                           int64_t N, int64_t V, int64_t K, int32_t* __restrict__ table) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  long long cell = -1;
+  if (i < N) {
+    const int64_t t = tokens[i], c = codes[i];
+    if (t >= 0 && t < V && c >= 0 && c < K) cell = t * K + c;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, cell);   // repeated (token, code) pairs inside a warp: one atomic
+  if (cell >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(table + cell, __popc(peers));
+}
+
+int launch_cooccurrence(const int64_t* tokens, const int64_t* codes, int64_t N, int64_t V, int64_t K, int32_t* table,
+                        cudaStream_t st) {
+  KVQ_CUDA(cudaMemsetAsync(table, 0, (size_t)V * (size_t)K * sizeof(int32_t), st));
+  if (N <= 0) return KVQ_OK;
+  cooccurrence_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(tokens, codes, N, V, K, table);
+  KVQ_LAUNCH_CHECK();
+  return KVQ_OK;
+}
+
 int launch_histogram(const int64_t* idx, int64_t N, int64_t K, int64_t k_offset, int32_t* hist, cudaStream_t st) {
   KVQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int32_t), st));
   if (N <= 0) return KVQ_OK;

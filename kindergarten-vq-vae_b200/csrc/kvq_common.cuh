@@ -128,6 +128,8 @@ int launch_backward(const float* z, const float* E, const int64_t* idx, const in
 size_t backward_workspace_bytes(int64_t N, int64_t K);
 int launch_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t numel,
                       double inv_nd, float* dz, cudaStream_t st);
+int launch_cooccurrence(const int64_t* tokens, const int64_t* codes, int64_t N, int64_t V, int64_t K, int32_t* table,
+                        cudaStream_t st);
 int launch_histogram(const int64_t* idx, int64_t N, int64_t K, int64_t k_offset, int32_t* hist, cudaStream_t st);
 int launch_kmeans_update(const float* z, const int64_t* idx, const int32_t* hist, int64_t N, int D, int64_t K,
                          const float* old_c, float* new_c, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -123,3 +123,32 @@ def test_kmeans2_matches_scipy_given_the_same_initial_centroids():
     assert d8 <= d3 * (1 + 1e-4)
     out = k.codebook_init_values(big.view(1024, 64, 256), 9, iter=2, seed=0)
     assert out["codebook_init_values"].shape == (9, 256) and not out["codebook_init_values"].is_cuda
+
+
+def test_code_usage_analysis_matches_python_loops():
+    """Device co-occurrence table vs the reference's nested-loop bookkeeping (unsupervised_vq_disentanglement.py:165-235)."""
+    k = _kvq()
+    A = k.analysis
+    gen = torch.Generator().manual_seed(9)
+    B, S, V, K = 64, 12, 50, 9
+    ids = torch.randint(0, V, (B, S), generator=gen)
+    codes = torch.randint(0, K - 1, (B, S, 1), generator=gen)            # code K-1 is never used
+    table = A.code_usage_by_token(ids.to(DEV), codes.to(DEV), V, K)
+    table = A.code_usage_by_token(ids.to(DEV), codes.to(DEV), V, K, table=table)      # accumulate a second "batch"
+    # reference-style bookkeeping
+    words = {t: f"w{t}" for t in range(V)}
+    interest = {"w3": 3, "w7": 7, "w49": 49}
+    seen, per_word, per_code = set(), {w: [] for w in interest}, {}
+    for _ in range(2):
+        for row_ids, row_codes in zip(ids.tolist(), codes.flatten(1).tolist()):
+            for t, c in zip(row_ids, row_codes):
+                seen.add(c); per_code.setdefault(c, set()).add(words[t])
+                if words[t] in interest:
+                    per_word[words[t]].append(c)
+    assert A.populated_codes(table) == seen and (K - 1) not in seen
+    hist = A.words_of_interest_histograms(table, interest)
+    for w in interest:
+        assert hist[w] == {c: per_word[w].count(c) for c in range(K)}
+    distrib = A.vq_words_distrib(table, words)
+    assert {c: sorted(v) for c, v in per_code.items()} == distrib
+    assert int(table.sum()) == 2 * B * S
