@@ -125,9 +125,11 @@ class BatchShardedVectorQuantizer(nn.Module):
 # ------------------------------------------------------------------------------------------------
 class _CodebookShardedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, E_local, beta, mode, group, k_offset, k_total, backend):
+    def forward(ctx, z, E_param, beta, mode, group, k_offset, k_total, backend):
         N, D = z.shape
         world = _world(group)
+        k_valid = max(0, min(E_param.shape[0], k_total - k_offset))     # rows past the end of the codebook are padding
+        E_local = E_param[:k_valid]
         _, keys = backend.search(z, E_local, mode=mode, k_offset=k_offset, want_idx=False, want_keys=True)
         if world > 1:
             dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)      # cross-GPU (distance, index) argmin
@@ -136,36 +138,48 @@ class _CodebookShardedFn(torch.autograd.Function):
         if world > 1:
             dist.all_reduce(z_q, op=dist.ReduceOp.SUM, group=group)       # each row is non-zero on exactly one rank
             dist.all_reduce(sq_sum, op=dist.ReduceOp.SUM, group=group)
-            per = E_local.shape[0]
+            per = E_param.shape[0]
+            padded = torch.zeros(per, dtype=hist_local.dtype, device=hist_local.device)
+            padded[:k_valid] = hist_local
             parts = [torch.empty(per, dtype=hist_local.dtype, device=hist_local.device) for _ in range(world)]
-            dist.all_gather(parts, hist_local.contiguous(), group=group)
+            dist.all_gather(parts, padded, group=group)
             hist = torch.cat(parts)[:k_total].contiguous()
         else:
             hist = hist_local
         loss, perplexity = backend.finalize(sq_sum, hist, N, D, beta)
         loss, perplexity = loss.clone(), perplexity.clone()
-        ctx.save_for_backward(z, E_local, idx, hist_local, z_q)
-        ctx.beta, ctx.k_offset, ctx.backend = beta, k_offset, backend
+        ctx.save_for_backward(z, E_param, idx, hist_local, z_q)
+        ctx.beta, ctx.k_offset, ctx.backend, ctx.k_valid = beta, k_offset, backend, k_valid
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(perplexity, idx, hist)
         return loss, z_q, perplexity, idx, hist
 
     @staticmethod
     def backward(ctx, g_loss, g_zq, *_):
-        z, E_local, idx, hist_local, z_q = ctx.saved_tensors
+        z, E_param, idx, hist_local, z_q = ctx.saved_tensors
         need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if g_zq is not None:
             g_zq = g_zq.contiguous()
         if g_loss is None:
-            return (g_zq if need_dz else None), (torch.zeros_like(E_local) if need_dE else None), None, None, None, \
+            return (g_zq if need_dz else None), (torch.zeros_like(E_param) if need_dE else None), None, None, None, \
                 None, None, None
         g_loss = g_loss.detach().to(torch.float32).contiguous()
         dz = ctx.backend.dz_from_zq(z, z_q, g_zq, g_loss, z.shape[0]) if need_dz else None
         dE = None
         if need_dE:   # local: only latents that chose one of this rank's codes contribute
-            _, dE = ctx.backend.vq_backward(z, E_local, idx, hist_local, ctx.beta, g_zq=None, g_loss=g_loss,
-                                            need_dz=False, need_dE=True, k_offset=ctx.k_offset)
+            dE = _local_codebook_grad(ctx.backend, z, E_param, ctx.k_valid, idx, hist_local, ctx.beta, g_loss, ctx.k_offset)
         return dz, dE, None, None, None, None, None, None
+
+
+def _local_codebook_grad(backend, z, E_param, k_valid, idx, hist_local, beta, g_loss, k_offset):
+    """dE of this rank's shard (padding rows, if any, get exact zeros)."""
+    _, dE = backend.vq_backward(z, E_param[:k_valid], idx, hist_local, beta, g_zq=None, g_loss=g_loss, need_dz=False,
+                                need_dE=True, k_offset=k_offset)
+    if k_valid == E_param.shape[0]:
+        return dE
+    full = torch.zeros_like(E_param)
+    full[:k_valid] = dE
+    return full
 
 
 class _PeerMemory:
@@ -195,12 +209,14 @@ class _CodebookShardedFusedFn(torch.autograd.Function):
     owner's shard through the peer mapping; three device-side barriers order the phases."""
 
     @staticmethod
-    def forward(ctx, z, E_local, beta, mode, peer: _PeerMemory, rank, world, k_offset, k_total):
+    def forward(ctx, z, E_param, beta, mode, peer: _PeerMemory, rank, world, k_offset, k_total):
         N, D = z.shape
-        k_per = E_local.shape[0]
+        k_per = E_param.shape[0]
+        k_valid = max(0, min(k_per, k_total - k_offset))
+        E_local = E_param[:k_valid]
         keys, kh = peer.keys_for(N)
         keys.fill_(torch.iinfo(torch.int64).max)
-        peer.mirror.copy_(E_local.detach())
+        peer.mirror.copy_(E_param.detach())
         kh.barrier(channel=0)                       # every rank's key buffer is initialised, every mirror refreshed
         _cuda_backend.search_peers(z, E_local, kh.buffer_ptrs, rank, mode=mode, k_offset=k_offset)
         kh.barrier(channel=1)                       # all remote atomics have landed: keys hold the global argmin
@@ -210,35 +226,34 @@ class _CodebookShardedFusedFn(torch.autograd.Function):
         hist = hist_all[:k_total].contiguous()
         loss, perplexity = _cuda_backend.finalize(sq_sum, hist, N, D, beta)
         loss, perplexity = loss.clone(), perplexity.clone()
-        hist_local = hist_all[k_offset:k_offset + k_per].contiguous()
-        ctx.save_for_backward(z, E_local, idx, hist_local, z_q)
-        ctx.beta, ctx.k_offset = beta, k_offset
+        hist_local = hist_all[k_offset:k_offset + k_valid].contiguous()
+        ctx.save_for_backward(z, E_param, idx, hist_local, z_q)
+        ctx.beta, ctx.k_offset, ctx.k_valid = beta, k_offset, k_valid
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(perplexity, idx, hist)
         return loss, z_q, perplexity, idx, hist
 
     @staticmethod
     def backward(ctx, g_loss, g_zq, *_):
-        z, E_local, idx, hist_local, z_q = ctx.saved_tensors
+        z, E_param, idx, hist_local, z_q = ctx.saved_tensors
         need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if g_zq is not None:
             g_zq = g_zq.contiguous()
         none = (None,) * 7
         if g_loss is None:
-            return ((g_zq if need_dz else None), (torch.zeros_like(E_local) if need_dE else None)) + none
+            return ((g_zq if need_dz else None), (torch.zeros_like(E_param) if need_dE else None)) + none
         g_loss = g_loss.detach().to(torch.float32).contiguous()
         dz = _cuda_backend.dz_from_zq(z, z_q, g_zq, g_loss, z.shape[0]) if need_dz else None
         dE = None
         if need_dE:
-            _, dE = _cuda_backend.vq_backward(z, E_local, idx, hist_local, ctx.beta, g_zq=None, g_loss=g_loss,
-                                              need_dz=False, need_dE=True, k_offset=ctx.k_offset)
+            dE = _local_codebook_grad(_cuda_backend, z, E_param, ctx.k_valid, idx, hist_local, ctx.beta, g_loss, ctx.k_offset)
         return (dz, dE) + none
 
 
 class CodebookShardedVectorQuantizer(nn.Module):
     """VectorQuantizer whose codebook rows are sharded over the ranks of `process_group` (latents replicated).
     `embedding` holds only this rank's shard: rows [k_offset, k_offset + k_local) of the global (n_e, e_dim)
-    codebook (all shards have ceil(n_e / world) rows; the tail of the last one is padding that can never win)."""
+    codebook (all shards have ceil(n_e / world) rows; the tail of the last one is padding the kernels never see)."""
 
     def __init__(self, n_e, e_dim, beta, vq_codebook_init_values: Tensor = None, *, process_group=None,
                  search: str = "auto", backend=None, exchange: str = "nccl"):
@@ -259,6 +274,8 @@ class CodebookShardedVectorQuantizer(nn.Module):
         self.k_offset = rank * self.k_per
         lo, hi = shard_bounds(n_e, world, rank)
         self.k_valid = hi - lo
+        if self.k_valid < 1:
+            raise ValueError(f"n_e={n_e} codes cannot be sharded over {world} ranks (rank {rank} would own none)")
         self.embedding = nn.Embedding(self.k_per, e_dim)
         with torch.no_grad():
             if vq_codebook_init_values is not None:
@@ -267,7 +284,7 @@ class CodebookShardedVectorQuantizer(nn.Module):
                 g = torch.Generator().manual_seed(0x5EED + rank)
                 self.embedding.weight.copy_((torch.rand(self.k_per, e_dim, generator=g) * 2 - 1) / n_e)
             if self.k_valid < self.k_per:
-                self.embedding.weight[self.k_valid:] = float("inf")   # padding rows: infinite distance
+                self.embedding.weight[self.k_valid:] = 0.0            # padding rows: never searched, zero gradient
 
     @torch.compiler.disable
     def forward(self, z: Tensor, device=None):

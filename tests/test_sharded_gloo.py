@@ -37,6 +37,8 @@ def _worker(rank, world, port, mode, q):
             out = dict(loss=loss.detach(), perp=perp, z_q=z_q.detach(), idx=idx, dz=zl.grad, dE=vq.embedding.weight.grad,
                        lo=lo, hi=hi)
         else:
+            if mode == "codebook_uneven":
+                E = E[:511].contiguous()            # 511 codes over 2 ranks: shards of 256 and 255 (+1 padding row)
             vq = CodebookShardedVectorQuantizer(E.shape[0], E.shape[1], beta, E, backend=cpu_backend)
             zl = z.clone().requires_grad_(True)
             loss, z_q, perp, _, idx = vq.forward(zl, "cpu")
@@ -90,3 +92,21 @@ def test_codebook_sharded_equals_single_device_reference():
         assert torch.allclose(res[r]["dz"], g["dz"], rtol=1e-4, atol=1e-6)
     dE = torch.cat([res[r]["dE"][: res[r]["k_valid"]] for r in sorted(res)])
     assert (dE - g["dE"]).abs().max() <= 2e-6 * g["dE"].abs().max()
+
+
+def test_codebook_sharded_uneven_shards():
+    from oracle import vq_oracle as O
+    g = load_golden("wide")
+    E = g["E"][:511].contiguous()
+    ref = O.forward_fp32(g["z"], E, float(g["beta"]))
+    dz, dE_ref = O.backward_closed_form(g["z"], E, ref.idx, float(g["beta"]), g_zq=g["gz"], g_loss=float(g["w"]))
+    res = _run("codebook_uneven")
+    assert res[0]["k_valid"] == 256 and res[1]["k_valid"] == 255
+    for r in res:
+        assert torch.equal(res[r]["idx"], ref.idx) and torch.equal(res[r]["z_q"], ref.z_q)
+        assert torch.allclose(res[r]["loss"], ref.loss, rtol=1e-6)
+        assert torch.allclose(res[r]["perp"], ref.perplexity, rtol=1e-5)
+        assert res[r]["dE"].shape[0] == 256                     # parameter keeps the padded shape
+    assert torch.all(res[1]["dE"][255] == 0)                    # padding row: exact zero gradient
+    dE = torch.cat([res[r]["dE"][: res[r]["k_valid"]] for r in sorted(res)])
+    assert (dE - dE_ref.float()).abs().max() <= 2e-6 * dE_ref.abs().max()
