@@ -111,6 +111,9 @@ SHAPES = [
     (8, 12, 768, 512, "default"),       # BERT latents, reference default init (streaming-operand path, D > 256)
     (8, 12, 768, 512, "normal"),
     (64, 64, 768, 512, "normal"),       # BASELINE config 1
+    (3, 50, 512, 300, "normal"),        # D = 512, 1024: streaming-operand path, widest rows of the bandwidth kernels
+    (2, 33, 1024, 64, "normal"),
+    (1, 5000, 32, 3000, "normal"),      # narrowest D the tensor-core kernel takes
     (2, 300, 256, 2048, "collapsed"),
     (1, 200, 256, 16384, "normal"),     # few latents, many codes: code-range split + atomicMin merge
 ]
