@@ -298,10 +298,10 @@ def run_kvq(args):
         roof = {"kernel": "search_tf32_kernel (tcgen05 distance+argmin)", "bound": "tensor", "achieved": ach,
                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the ncu --set full
-                # capture profiles/r01/ncu_search_v3.summary.csv (4.525 GB + 24.5 MB); algorithmic HBM bytes are 1.15 GB
-                # -- the 64 MB codebook is re-read from HBM on each of the ~55 sweeps per SM pair (107 GB/s, irrelevant
-                # to a tensor-bound kernel)
-                "traffic": 4.549e9 if (n_rows == 1 << 20 and K == 65536) else None,
+                # capture profiles/r01/ncu_full_final_kernels.summary.csv (4.637 GB + 24.7 MB); algorithmic HBM bytes are
+                # 1.15 GB -- the 64 MB codebook is re-read from HBM on each of the ~55 sweeps per SM pair (121 GB/s,
+                # irrelevant to a tensor-bound kernel: tensor pipe 97.7 % active in the same capture)
+                "traffic": 4.662e9 if (n_rows == 1 << 20 and K == 65536) else None,
                 "cublas_tf32_tflops_live": cublas_tf32,
                 "peak_source": f"{pk['source']} bf16 dense {'sustained' if sustained else 'burst'} / 2 "
                                "(tf32 runs at half the bf16 rate; tf32 itself is not in MEASURED_PEAKS.json)",
@@ -311,13 +311,17 @@ def run_kvq(args):
         b = 3 * 4.0 * n_rows * D + 8.0 * n_rows + 4.0 * K
         others["quantize"] = {"bound": "hbm", "achieved": b / (prof["quantize"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                               "unit": "GB/s", "frac": b / (prof["quantize"] * 1e-3) / 1e9 / pk["hbm_gbs"],
-                              "algorithmic_bytes_per_launch": b, "ms_per_launch": prof["quantize"]}
+                              "algorithmic_bytes_per_launch": b, "ms_per_launch": prof["quantize"],
+                              "traffic": 2.227e9 if (n_rows == 1 << 20 and K == 65536) else None,
+                              "note": "algorithmic bytes count the gathered codebook rows (4ND) as HBM reads; they are "
+                                      "L2 hits, measured DRAM traffic is 2.23 GB = 6.3 TB/s (ncu, profiles/r01)"}
     if prof["bwd_segmented"]:
         b = 3 * 4.0 * n_rows * D + 8.0 * n_rows + 4.0 * K * D
         others["bwd_segmented"] = {"bound": "hbm", "achieved": b / (prof["bwd_segmented"] * 1e-3) / 1e9,
                                    "peak": pk["hbm_gbs"], "unit": "GB/s",
                                    "frac": b / (prof["bwd_segmented"] * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                   "algorithmic_bytes_per_launch": b, "ms_per_launch": prof["bwd_segmented"]}
+                                   "algorithmic_bytes_per_launch": b, "ms_per_launch": prof["bwd_segmented"],
+                                   "traffic": 3.267e9 if (n_rows == 1 << 20 and K == 65536) else None}
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only) ---------------------------------------------
     cpu = None
