@@ -117,6 +117,34 @@ class ClockSampler:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0, note=f"no clock source: {exc}")
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers allocated
+    afterwards are node-local (one process per GPU: without this every rank's staging memory may sit on socket 0
+    and all host<->device copies cross the inter-socket link).  Measurement plumbing; returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # 00000000:1B:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return f"gpu {index} ({bus}): no NUMA affinity reported"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return f"gpu {index} ({bus}): node {node} has no allowed CPUs"
+        os.sched_setaffinity(0, allowed)
+        return f"gpu {index} ({bus}) -> NUMA node {node}, {len(allowed)} CPUs"
+    except Exception as exc:                      # no NVML / sysfs: leave the default placement
+        return f"not bound ({exc})"
+
+
 # ---------------------------------------------------------------------------------------------------------
 def synth_device(torch, dev, n_rows, seed):
     """Seeded synthetic inputs: z, g_zq ~ N(0,1); data-scale codebook = K latents + noise
@@ -180,6 +208,7 @@ def run_kvq(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- kvq has no CPU path (use --impl reference for the CPU arm)")
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single process: default placement"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -345,7 +374,7 @@ def run_kvq(args):
                        "codebook_init": "data-scale: N(0,1) rows + 0.1 noise"},
             "roofline": roof, "roofline_other_kernels": others, "kernel_ms": prof,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp), "index_parity": parity,
+            "host_placement": numa, "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp), "index_parity": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
