@@ -271,7 +271,7 @@ def literal_step_cpu(z: torch.Tensor, E: torch.Tensor, beta: float, g_zq: torch.
 
 class LiteralVectorQuantizer(torch.nn.Module):
     """The reference layer restated as a module (same ops as `literal_step_cpu`, any device): the A/B partner of
-    the kvq module in tools/shelgon_step.py on machines where /root/reference is not mounted.  TEST INFRASTRUCTURE."""
+    the kvq module in tests/harness_shelgon_step.py on machines where /root/reference is not mounted.  TEST INFRASTRUCTURE."""
 
     def __init__(self, n_e, e_dim, beta, vq_codebook_init_values=None):
         super().__init__()

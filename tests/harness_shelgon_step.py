@@ -5,7 +5,7 @@
 restated here because the reference's own classes do not construct at HEAD and need network
 access for pretrained weights.  The same model is stepped twice from identical seeds: once with the kvq
 VectorQuantizer, once with a literal PyTorch restatement of the reference layer; losses, indices and step times are
-compared.  Measurement script, not product code.
+compared.  Test harness (it uses the oracle as the A/B partner), not product code.
 """
 import json
 import os
