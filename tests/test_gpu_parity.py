@@ -255,3 +255,47 @@ def test_large_properties(N, D, K, init):
     ref = torch.zeros(K, D, device=DEV, dtype=torch.float64).index_add_(0, idx, (q - z).double()) * (c1 * beta)
     assert float((dE.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
     assert bool((dE[hist == 0] == 0).all())                                   # dense gradient, exact zeros
+
+
+def test_cuda_graph_capture_and_replay():
+    """The library never synchronises or allocates, so a whole forward + backward of the layer captures into one
+    CUDA graph; replays with new inputs in the same buffers must equal eager results."""
+    k = _kvq()
+    z0, E, gz0 = _seeded(8, 12, 768, 512, "normal", seed=5)
+    z1, _, gz1 = _seeded(8, 12, 768, 512, "normal", seed=6)
+    vq = k.VectorQuantizer(512, 768, 0.25, vq_codebook_init_values=E, min_encodings=False).to(DEV)
+    zs = z0.to(DEV).requires_grad_(True)
+    gs = gz0.to(DEV).clone()
+    one = torch.ones((), device=DEV)
+
+    def step():
+        zs.grad = None
+        vq.embedding.weight.grad = None
+        loss, z_q, perp, _, idx = vq.forward(zs, DEV)
+        torch.autograd.backward([loss, z_q], [one, gs])
+        return loss, z_q, perp, idx
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    zs.grad = None
+    vq.embedding.weight.grad = None
+    with torch.cuda.graph(graph):
+        loss_g, zq_g, perp_g, idx_g = step()
+        dz_g, dE_g = zs.grad, vq.embedding.weight.grad
+    for zin, gin in ((z0, gz0), (z1, gz1)):
+        with torch.no_grad():
+            zs.copy_(zin.to(DEV)); gs.copy_(gin.to(DEV))
+        graph.replay()
+        torch.cuda.synchronize()
+        got = dict(loss=loss_g.detach().cpu().clone(), z_q=zq_g.detach().cpu().clone(), perplexity=perp_g.cpu().clone(),
+                   idx=idx_g.cpu().clone(), dz=dz_g.cpu().clone(), dE=dE_g.cpu().clone())
+        ref = run_module(zin, E, 0.25, gin, 1.0, search="auto", min_encodings=False)
+        assert torch.equal(got["idx"], ref["idx"]) and torch.equal(got["z_q"], ref["z_q"])
+        assert abs(float(got["loss"]) - float(ref["loss"])) <= 1e-6 * float(ref["loss"])
+        assert torch.allclose(got["dz"], ref["dz"], rtol=1e-6, atol=1e-8)
+        assert (got["dE"] - ref["dE"]).abs().max() <= 1e-5 * ref["dE"].abs().max()

@@ -79,6 +79,16 @@ def single():
             out = dict(config=name, N=N, D=D, K=K, init=init, ms_fwd_bwd=ms, latents_per_s=N / ms * 1e3, kernel_ms=prof)
             if prof["search"]:
                 out["search_tflops"] = 2.0 * N * K * D / prof["search"] / 1e9
+            if N <= 32768:   # small shapes are launch-bound: the same step as ONE CUDA-graph launch
+                side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    step()
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                z3.grad = None; vq.embedding.weight.grad = None
+                with torch.cuda.graph(graph):
+                    step()
+                out["ms_fwd_bwd_cuda_graph"] = timed(graph.replay, iters=200)
             print(json.dumps(out), flush=True)
             del vq, z, gz, E, z3, g3
 
