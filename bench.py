@@ -27,7 +27,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "vq_latents_per_sec_fwd_bwd"
+METRIC = "VQ latents/sec (fwd+bwd) at K=65536,D=256"
 UNIT = "latents/s"
 N_PER_GPU = 1 << 20
 D = 256
