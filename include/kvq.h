@@ -39,7 +39,10 @@ enum {
 enum {
   KVQ_SEARCH_AUTO = 0,  /* tf32 tensor-core search when the shape allows (D % 32 == 0), else fp32 */
   KVQ_SEARCH_TF32 = 1,  /* TMA-fed tcgen05.mma.kind::tf32, fp32 accumulate in TMEM, fused argmin epilogue */
-  KVQ_SEARCH_FP32 = 2   /* CUDA-core fp32 FMA search (exact-precision mode, any D % 4 == 0) */
+  KVQ_SEARCH_FP32 = 2,  /* CUDA-core fp32 FMA search (exact-precision mode, any D % 4 == 0) */
+  KVQ_SEARCH_TF32_REFINE = 3  /* tensor-core search keeping the two best codes per latent, then an exact float64
+                                 re-evaluation of that pair: tf32 speed, index mismatches vs an exact argmin only when
+                                 the true winner was not among the tf32 top two (unsharded searches only) */
 };
 
 int kvq_version(void);

@@ -13,9 +13,9 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libkvq.so")
 
 KVQ_OK = 0
-SEARCH_AUTO, SEARCH_TF32, SEARCH_FP32 = 0, 1, 2
+SEARCH_AUTO, SEARCH_TF32, SEARCH_FP32, SEARCH_TF32_REFINE = 0, 1, 2, 3
 PROF_TAGS = ["norms", "search", "quantize", "finalize", "bwd_bucket", "bwd_segmented"]
-SEARCH_MODES = {"auto": SEARCH_AUTO, "tf32": SEARCH_TF32, "fp32": SEARCH_FP32}
+SEARCH_MODES = {"auto": SEARCH_AUTO, "tf32": SEARCH_TF32, "fp32": SEARCH_FP32, "tf32_refine": SEARCH_TF32_REFINE}
 
 _P = c_void_p
 

@@ -98,9 +98,27 @@ static int resolve_mode(int mode, int64_t N, int D, int64_t K, int* out) {
     KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (D=%d)", D);
     *out = mode; return KVQ_OK;
   }
+  if (mode == KVQ_SEARCH_TF32_REFINE) {
+    KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32_refine search needs D %% 32 == 0 (D=%d)", D);
+    *out = mode; return KVQ_OK;
+  }
   KVQ_REQUIRE(mode == KVQ_SEARCH_FP32, KVQ_ERR_ARG, "unknown search mode %d", mode);
   *out = mode;
   return KVQ_OK;
+}
+
+int run_search(int mode, const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t* idx,
+               long long* scratch, cudaStream_t st) {
+  if (mode == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, e2, N, D, K, 0, idx, scratch, 0, st);
+  if (mode == KVQ_SEARCH_TF32_REFINE && !tf32_search_splits(N, K)) {
+    // tensor-core search keeping the two best codes per latent, then an exact float64 re-evaluation of the pair
+    int64_t* runner_up = reinterpret_cast<int64_t*>(scratch);
+    int rc = launch_search_tf32_top2(z, E, e2, N, D, K, idx, runner_up, st);
+    if (rc) return rc;
+    return launch_refine_top2(z, E, N, D, idx, runner_up, st);
+  }
+  // fp32 mode, and tf32_refine on shapes small enough that the search would be split over CTAs (exact and cheap there)
+  return launch_search_fp32(z, E, e2, N, D, K, 0, idx, scratch, 0, st);
 }
 
 }  // namespace kvq
@@ -178,6 +196,11 @@ int kvq_search(const float* z, const float* E, int64_t N, int D, int64_t K, int6
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); if (rc) return rc;
   long long* kbuf = keys ? reinterpret_cast<long long*>(keys) : w.keys;  // internal keys only for split searches
+  if (m == KVQ_SEARCH_TF32_REFINE) {
+    KVQ_REQUIRE(k_offset == 0 && !keys && idx, KVQ_ERR_UNSUPPORTED,
+                "kvq_search: tf32_refine is for unsharded searches that return indices (no keys, k_offset 0)");
+    return run_search(m, z, E, w.e2, N, D, K, idx, w.keys, st);
+  }
   if (m == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
   return launch_search_fp32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
 }
@@ -258,8 +281,7 @@ int kvq_forward(const float* z, const float* E, int64_t N, int D, int64_t K, flo
   cudaStream_t st = (cudaStream_t)stream;
   { ProfScope ps(KVQ_PROF_NORMS, st); rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); }
   if (rc) return rc;
-  if (m == KVQ_SEARCH_TF32) rc = launch_search_tf32(z, E, w.e2, N, D, K, 0, idx, w.keys, 0, st);
-  else rc = launch_search_fp32(z, E, w.e2, N, D, K, 0, idx, w.keys, 0, st);
+  rc = run_search(m, z, E, w.e2, N, D, K, idx, w.keys, st);
   if (rc) return rc;
   KVQ_CUDA(cudaMemsetAsync(w.sq_sum, 0, sizeof(double), st));
   KVQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int32_t), st));

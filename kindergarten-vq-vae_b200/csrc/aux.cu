@@ -219,10 +219,7 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   for (int64_t c = 0; c < chunks && status == KVQ_OK; ++c) {
     const int64_t r0 = c * rows_per_chunk, rows = (N - r0 < rows_per_chunk) ? (N - r0) : rows_per_chunk;
     KVQ_TRYC(cudaStreamWaitEvent(hp.s_cmp, ev_in[c], 0));
-    if (m == KVQ_SEARCH_TF32)
-      KVQ_TRY(launch_search_tf32(hp.z + r0 * D, hp.E, e2, rows, D, K, 0, hp.idx + r0, keys + r0, 0, hp.s_cmp));
-    else
-      KVQ_TRY(launch_search_fp32(hp.z + r0 * D, hp.E, e2, rows, D, K, 0, hp.idx + r0, keys + r0, 0, hp.s_cmp));
+    KVQ_TRY(run_search(m, hp.z + r0 * D, hp.E, e2, rows, D, K, hp.idx + r0, keys + r0, hp.s_cmp));
     KVQ_TRY(launch_quantize(hp.z + r0 * D, hp.E, hp.idx + r0, rows, D, K, 0, 0, hp.zq + r0 * D, sq_sum, hist, hp.s_cmp));
     // dz depends only on this chunk's rows and the (host-given) loss weight: compute it now so that its
     // device->host copy overlaps the search of the next chunk.

@@ -61,6 +61,44 @@ int launch_keys_to_idx(const long long* keys, int64_t N, int64_t* idx, cudaStrea
 }
 
 // ------------------------------------------------------------------------------------------------
+// exact re-evaluation of the tensor-core search's two best candidates ("tf32_refine" search mode).
+// One warp per latent: |z - E_a|^2 and |z - E_b|^2 accumulated in float64 from the fp32 inputs (exact differences),
+// winner = smaller distance, ties -> lower index.  Reads 4D bytes of z per latent; the two codebook rows are L2 hits.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) refine_top2_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                          int64_t N, int D, int64_t* __restrict__ idx,
+                                                          const int64_t* __restrict__ idx2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int64_t a = idx[row], b = idx2[row];
+  if (a == b) return;
+  const float4* zr = reinterpret_cast<const float4*>(z + row * D);
+  const float4* ea = reinterpret_cast<const float4*>(E + a * D);
+  const float4* eb = reinterpret_cast<const float4*>(E + b * D);
+  double da = 0.0, db = 0.0;
+  for (int v = lane; v < (D >> 2); v += 32) {
+    const float4 x = ld_stream(zr + v), p = __ldg(ea + v), q = __ldg(eb + v);
+    double t;
+    t = (double)x.x - (double)p.x; da += t * t;  t = (double)x.y - (double)p.y; da += t * t;
+    t = (double)x.z - (double)p.z; da += t * t;  t = (double)x.w - (double)p.w; da += t * t;
+    t = (double)x.x - (double)q.x; db += t * t;  t = (double)x.y - (double)q.y; db += t * t;
+    t = (double)x.z - (double)q.z; db += t * t;  t = (double)x.w - (double)q.w; db += t * t;
+  }
+  da = warp_sum(da);
+  db = warp_sum(db);
+  if (lane == 0 && (db < da || (db == da && b < a))) idx[row] = b;
+}
+
+int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2, cudaStream_t st) {
+  if (N <= 0) return KVQ_OK;
+  const int wpb = 8;
+  refine_top2_kernel<<<(unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st>>>(z, E, N, D, idx, idx2);
+  KVQ_LAUNCH_CHECK();
+  return KVQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // gather + straight-through + squared-residual sum + usage histogram.
 //
 // One warp owns 32 consecutive latents.  Lane j first reads idx[row0+j] (one coalesced 256-B read) and the

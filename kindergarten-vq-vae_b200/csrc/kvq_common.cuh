@@ -115,6 +115,13 @@ int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t 
                        int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st,
                        const PeerKeys* peers = nullptr);
 bool tf32_shape_ok(int64_t N, int D, int64_t K);
+bool tf32_search_splits(int64_t N, int64_t K);
+int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
+                            int64_t* idx, int64_t* idx2, cudaStream_t st);
+int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2, cudaStream_t st);
+// unsharded search in any mode (AUTO already resolved): idx out; `scratch` = N int64 (keys / runner-up indices)
+int run_search(int mode, const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t* idx,
+               long long* scratch, cudaStream_t st);
 int launch_fill_keys(long long* keys, int64_t N, cudaStream_t st);
 int launch_keys_to_idx(const long long* keys, int64_t N, int64_t* idx, cudaStream_t st);
 int launch_quantize(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int64_t K,

@@ -69,6 +69,7 @@ struct Params {
   int use_atomic;       // MIN-combine into keys (split code range or caller-accumulated keys)
   const float* e2;      // padded to n_tiles*256 with +inf
   int64_t* idx;
+  int64_t* idx2;        // TOP2 kernels: runner-up code per latent (for the exact re-evaluation pass)
   long long* keys;
   PeerKeys peers;       // n > 0: MIN-combine the packed keys straight into every rank's buffer over NVLink
 };
@@ -247,8 +248,54 @@ __device__ __forceinline__ void argmin_batch(const uint32_t (&acc)[32], const fl
   }
 }
 
+// Running top-2 of one latent row.  The overall runner-up is either the best of some OTHER 32-column batch (ov, oi)
+// or the second best inside the batch that holds the winner (b2v, b2i); both are maintained in the rare paths only.
+struct Top2 {
+  float bv, b2v, ov;
+  uint32_t bi, b2i, oi;
+};
+__device__ __forceinline__ void argmin_batch_top2(const uint32_t (&acc)[32], const float4* __restrict__ e2v,
+                                                  uint32_t col_base, Top2& t) {
+  float s[32];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 en = __ldg(e2v + j4);
+    s[j4 * 4 + 0] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 0]), en.x);
+    s[j4 * 4 + 1] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 1]), en.y);
+    s[j4 * 4 + 2] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 2]), en.z);
+    s[j4 * 4 + 3] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 3]), en.w);
+  }
+  float u[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) u[i] = fmin3(s[3 * i], s[3 * i + 1], s[3 * i + 2]);
+  u[10] = fminf(s[30], s[31]);
+  const float m = fminf(fmin3(fmin3(u[0], u[1], u[2]), fmin3(u[3], u[4], u[5]), fmin3(u[6], u[7], u[8])), fminf(u[9], u[10]));
+  if (m < t.bv) {
+    // the previous winner becomes a candidate of the "other batches" slot (its own batch's runner-up cannot beat it)
+    if (t.bv < t.ov || (t.bv == t.ov && t.bi < t.oi)) { t.ov = t.bv; t.oi = t.bi; }
+    int j = 31;
+#pragma unroll
+    for (int jj = 30; jj >= 0; --jj) j = (s[jj] == m) ? jj : j;
+    t.bv = m;
+    t.bi = col_base + (uint32_t)j;
+    float r = INFINITY;
+    int rj = 0;
+#pragma unroll
+    for (int jj = 31; jj >= 0; --jj)
+      if (jj != j && s[jj] <= r) { r = s[jj]; rj = jj; }     // '<=' while walking down: first index wins ties
+    t.b2v = r;
+    t.b2i = col_base + (uint32_t)rj;
+  } else if (m < t.ov) {
+    int j = 31;
+#pragma unroll
+    for (int jj = 30; jj >= 0; --jj) j = (s[jj] == m) ? jj : j;
+    t.ov = m;
+    t.oi = col_base + (uint32_t)j;
+  }
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------
-template <int CG>
+template <int CG, bool TOP2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
                    const Params p) {
@@ -426,6 +473,9 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
       const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
       float bv = INFINITY;
       uint32_t bi = (uint32_t)(t_begin * BLOCK_N + half * 128);
+      Top2 t2;
+      t2.bv = t2.b2v = t2.ov = INFINITY;
+      t2.bi = t2.b2i = t2.oi = bi;
 
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(bar_tm_full + 8 * acc, acc_phase);
@@ -439,13 +489,13 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
         tmem_ld32_async(taddr, ra);
         tmem_wait_ld(ra);
         tmem_ld32_async(taddr + 32, rb);
-        argmin_batch(ra, e2v, col0, bv, bi);
+        if constexpr (TOP2) argmin_batch_top2(ra, e2v, col0, t2); else argmin_batch(ra, e2v, col0, bv, bi);
         tmem_wait_ld(rb);
         tmem_ld32_async(taddr + 64, ra);
-        argmin_batch(rb, e2v + 8, col0 + 32, bv, bi);
+        if constexpr (TOP2) argmin_batch_top2(rb, e2v + 8, col0 + 32, t2); else argmin_batch(rb, e2v + 8, col0 + 32, bv, bi);
         tmem_wait_ld(ra);
         tmem_ld32_async(taddr + 96, rb);
-        argmin_batch(ra, e2v + 16, col0 + 64, bv, bi);
+        if constexpr (TOP2) argmin_batch_top2(ra, e2v + 16, col0 + 64, t2); else argmin_batch(ra, e2v + 16, col0 + 64, bv, bi);
         tmem_wait_ld(rb);
         tc_fence_before();
         __syncwarp();
@@ -453,9 +503,17 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
           if constexpr (CG == 2) mbar_arrive_cluster(map_to_cta(bar_tm_empty + 8 * acc, 0));
           else mbar_arrive(bar_tm_empty + 8 * acc);
         }
-        argmin_batch(rb, e2v + 24, col0 + 96, bv, bi);
+        if constexpr (TOP2) argmin_batch_top2(rb, e2v + 24, col0 + 96, t2); else argmin_batch(rb, e2v + 24, col0 + 96, bv, bi);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+      }
+      float sv = INFINITY;            // runner-up (TOP2 only)
+      uint32_t si = bi;
+      if constexpr (TOP2) {
+        bv = t2.bv; bi = t2.bi;
+        const bool other = (t2.ov < t2.b2v) || (t2.ov == t2.b2v && t2.oi < t2.b2i);
+        sv = other ? t2.ov : t2.b2v;
+        si = other ? t2.oi : t2.b2i;
       }
       // merge the two column halves through shared memory
       if (half == 1) { merge_val[row_in_tile] = bv; merge_idx[row_in_tile] = bi; }
@@ -463,8 +521,29 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
       if (half == 0) {
         const float ov = merge_val[row_in_tile];
         const uint32_t oi = merge_idx[row_in_tile];
-        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        float ov2 = INFINITY;
+        uint32_t oi2 = oi;
+        if constexpr (TOP2) {           // second round through the same scratch: the other half's runner-up
+          asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+          ov2 = merge_val[row_in_tile];
+          oi2 = merge_idx[row_in_tile];
+        }
+        if (ov < bv || (ov == bv && oi < bi)) {
+          // the other half holds the winner: runner-up = better of (our winner, their runner-up)
+          if constexpr (TOP2) {
+            const bool theirs = (ov2 < bv) || (ov2 == bv && oi2 < bi);
+            sv = theirs ? ov2 : bv;
+            si = theirs ? oi2 : bi;
+          }
+          bv = ov; bi = oi;
+        } else if constexpr (TOP2) {    // we hold the winner: runner-up = better of (their winner, our runner-up)
+          if (ov < sv || (ov == sv && oi < si)) { sv = ov; si = oi; }
+        }
         const int64_t row = (m_group * CG + cta_rank) * BLOCK_M + row_in_tile;
+        if constexpr (TOP2) {
+          if (row < p.N && p.idx2) p.idx2[row] = (int64_t)((sv < INFINITY ? si : bi) + p.k_offset);
+        }
         if (row < p.N) {
           const uint32_t gi = (uint32_t)(bi + p.k_offset);
           const long long key = pack_key(bv, gi);
@@ -482,6 +561,12 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
             if (p.idx) p.idx[row] = (int64_t)gi;
           }
         }
+      }
+      else if constexpr (TOP2) {      // half 1: publish the runner-up once half 0 has read the winner
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+        merge_val[row_in_tile] = sv;
+        merge_idx[row_in_tile] = si;
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
       }
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
     }
@@ -539,9 +624,10 @@ static int env_int(const char* name, int dflt) {
   return (e && e[0]) ? atoi(e) : dflt;
 }
 
-template <int CG>
+template <int CG, bool TOP2>
 static int launch_cg(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t k_offset,
-                     int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st, const PeerKeys* peers) {
+                     int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st, const PeerKeys* peers,
+                     int64_t* idx2) {
   constexpr int B_STAGE_BYTES = (BLOCK_N / CG) * BLOCK_K * 4;
   Params p;
   p.N = N; p.K = K; p.k_offset = k_offset; p.D = D;
@@ -565,8 +651,10 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   KVQ_REQUIRE(stages >= 2, KVQ_ERR_SHAPE, "tf32 search: no room for a 2-stage ring at D=%d", D);
   p.stages = stages;
   p.use_atomic = (p.ksplit > 1 || keys_accumulate) ? 1 : 0;
-  p.e2 = e2; p.idx = idx; p.keys = keys;
+  p.e2 = e2; p.idx = idx; p.keys = keys; p.idx2 = idx2;
   if (peers) p.peers = *peers; else p.peers.n = 0;
+  if (TOP2) KVQ_REQUIRE(p.ksplit == 1 && !p.use_atomic && p.peers.n == 0 && idx && idx2, KVQ_ERR_UNSUPPORTED,
+                        "tf32 top-2 search needs an unsplit, unsharded search");
   KVQ_REQUIRE(p.peers.n > 0 || !p.use_atomic || keys, KVQ_ERR_ARG,
               "kvq_search(tf32): split/accumulate search needs a keys buffer");
   const size_t smem = 1024 + SMEM_CTRL_BYTES + (size_t)a_bytes + (size_t)stages * stage_bytes;
@@ -582,7 +670,7 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
     rc = launch_fill_keys(keys, N, st);
     if (rc) return rc;
   }
-  KVQ_CUDA(cudaFuncSetAttribute(search_tf32_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KVQ_CUDA(cudaFuncSetAttribute(search_tf32_kernel<CG, TOP2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)(min_i64(p.n_items, groups) * CG);
   {
     ProfScope ps(KVQ_PROF_SEARCH, st);
@@ -599,7 +687,7 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     count_launch();
-    KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG>, mz, me, p));
+    KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG, TOP2>, mz, me, p));
   }
   if (p.peers.n == 0 && p.use_atomic && idx && !keys_accumulate) return launch_keys_to_idx(keys, N, idx, st);
   return KVQ_OK;
@@ -620,8 +708,23 @@ int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t 
   KVQ_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)E & 15) == 0, KVQ_ERR_ARG,
               "tf32 search needs 16-byte aligned z and E (TMA)");
   static const int cta_group = t5::env_int("KVQ_TF32_CTA_GROUP", 2);
-  if (cta_group == 1) return t5::launch_cg<1>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers);
-  return t5::launch_cg<2>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers);
+  if (cta_group == 1) return t5::launch_cg<1, false>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers, nullptr);
+  return t5::launch_cg<2, false>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers, nullptr);
+}
+
+// Would the tensor-core search split the code range over CTAs for this shape?  (Then the top-2 variant is not used.)
+bool tf32_search_splits(int64_t N, int64_t K) {
+  const int64_t m_groups = ((N + t5::BLOCK_M - 1) / t5::BLOCK_M + 1) / 2;
+  return m_groups < sm_count() / 2 && K > t5::BLOCK_N;
+}
+
+int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
+                            int64_t* idx, int64_t* idx2, cudaStream_t st) {
+  if (N <= 0) return KVQ_OK;
+  KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (got D=%d)", D);
+  KVQ_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)E & 15) == 0, KVQ_ERR_ARG,
+              "tf32 search needs 16-byte aligned z and E (TMA)");
+  return t5::launch_cg<2, true>(z, E, e2, N, D, K, 0, idx, nullptr, 0, st, nullptr, idx2);
 }
 
 }  // namespace kvq

@@ -72,7 +72,8 @@ class VectorQuantizer(nn.Module):
     - vq_codebook_init_values : optional (n_e, e_dim) initial codebook (e.g. from k-means)
 
     Extra keyword-only options (not in the reference):
-    - search : "auto" | "tf32" | "fp32" -- precision of the nearest-code search
+    - search : "auto" | "tf32" | "fp32" | "tf32_refine" -- precision of the nearest-code search ("tf32_refine":
+               tensor-core search for the two best codes, exact float64 re-evaluation of that pair)
     - min_encodings : "auto" | True | False -- when to materialise the dense one-hot output
     """
 
@@ -82,8 +83,8 @@ class VectorQuantizer(nn.Module):
         self.n_e = n_e
         self.e_dim = e_dim
         self.beta = beta
-        if search not in ("auto", "tf32", "fp32"):
-            raise ValueError(f"search must be auto|tf32|fp32, got {search!r}")
+        if search not in ("auto", "tf32", "fp32", "tf32_refine"):
+            raise ValueError(f"search must be auto|tf32|fp32|tf32_refine, got {search!r}")
         self.search = search
         self.return_min_encodings = min_encodings
 
