@@ -37,7 +37,8 @@ enum {
 
 /* Search precision (argument `mode`). */
 enum {
-  KVQ_SEARCH_AUTO = 0,  /* tf32 tensor-core search when the shape allows (D % 32 == 0), else fp32 */
+  KVQ_SEARCH_AUTO = 0,  /* D % 32 == 0: TF32_REFINE for unsharded searches that return indices, TF32 for sharded /
+                           key-emitting ones; otherwise FP32 */
   KVQ_SEARCH_TF32 = 1,  /* TMA-fed tcgen05.mma.kind::tf32, fp32 accumulate in TMEM, fused argmin epilogue */
   KVQ_SEARCH_FP32 = 2,  /* CUDA-core fp32 FMA search (exact-precision mode, any D % 4 == 0) */
   KVQ_SEARCH_TF32_REFINE = 3  /* tensor-core search keeping the two best codes per latent, then an exact float64

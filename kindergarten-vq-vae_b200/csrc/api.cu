@@ -92,8 +92,13 @@ static int check_shape(const char* who, int64_t N, int D, int64_t K) {
   return KVQ_OK;
 }
 
-static int resolve_mode(int mode, int64_t N, int D, int64_t K, int* out) {
-  if (mode == KVQ_SEARCH_AUTO) { *out = tf32_shape_ok(N, D, K) ? KVQ_SEARCH_TF32 : KVQ_SEARCH_FP32; return KVQ_OK; }
+// AUTO = tensor-core search with the exact re-evaluation of the two best codes where that applies (unsharded search
+// returning indices), plain tensor-core search for sharded / key-emitting searches, fp32 when D % 32 != 0.
+static int resolve_mode(int mode, int64_t N, int D, int64_t K, int* out, bool allow_refine = true) {
+  if (mode == KVQ_SEARCH_AUTO) {
+    *out = !tf32_shape_ok(N, D, K) ? KVQ_SEARCH_FP32 : (allow_refine ? KVQ_SEARCH_TF32_REFINE : KVQ_SEARCH_TF32);
+    return KVQ_OK;
+  }
   if (mode == KVQ_SEARCH_TF32) {
     KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (D=%d)", D);
     *out = mode; return KVQ_OK;
@@ -192,7 +197,7 @@ int kvq_search(const float* z, const float* E, int64_t N, int D, int64_t K, int6
   FwdWs w = carve_forward(ws, N, K);
   KVQ_REQUIRE(ws_bytes >= w.bytes, KVQ_ERR_WORKSPACE, "kvq_search: workspace %zu < %zu bytes", ws_bytes, w.bytes);
   KVQ_REQUIRE(!keys_accumulate || keys, KVQ_ERR_ARG, "kvq_search: keys_accumulate needs keys");
-  int m; rc = resolve_mode(mode, N, D, K, &m); if (rc) return rc;
+  int m; rc = resolve_mode(mode, N, D, K, &m, /*allow_refine=*/k_offset == 0 && !keys && idx); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); if (rc) return rc;
   long long* kbuf = keys ? reinterpret_cast<long long*>(keys) : w.keys;  // internal keys only for split searches
@@ -221,7 +226,8 @@ int kvq_search_peers(const float* z, const float* E, int64_t N, int D, int64_t K
   for (int g = 0; g < n_peers; ++g) KVQ_REQUIRE(pk.p[g], KVQ_ERR_ARG, "kvq_search_peers: peer %d has a null key buffer", g);
   pk.n = n_peers;
   pk.first = (my_rank + 1) % n_peers;
-  int m; rc = resolve_mode(mode, N, D, K, &m); if (rc) return rc;
+  int m; rc = resolve_mode(mode, N, D, K, &m, /*allow_refine=*/false); if (rc) return rc;
+  KVQ_REQUIRE(m != KVQ_SEARCH_TF32_REFINE, KVQ_ERR_UNSUPPORTED, "kvq_search_peers: tf32_refine is for unsharded searches");
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); if (rc) return rc;
   if (m == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, w.e2, N, D, K, k_offset, nullptr, nullptr, 0, st, &pk);

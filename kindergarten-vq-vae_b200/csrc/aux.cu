@@ -168,7 +168,7 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   HostPipe& hp = g_pipe;
   rc = ensure_pipe(hp, N, D, K); if (rc) return rc;
   int m = mode;
-  if (m == KVQ_SEARCH_AUTO) m = tf32_shape_ok(N, D, K) ? KVQ_SEARCH_TF32 : KVQ_SEARCH_FP32;
+  if (m == KVQ_SEARCH_AUTO) m = tf32_shape_ok(N, D, K) ? KVQ_SEARCH_TF32_REFINE : KVQ_SEARCH_FP32;
 
   // workspace pieces (same carving as kvq_forward): e2 | keys | sq_sum
   const int64_t K_pad = (K + SEARCH_TILE_N - 1) / SEARCH_TILE_N * SEARCH_TILE_N;
