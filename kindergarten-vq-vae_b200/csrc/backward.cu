@@ -461,19 +461,18 @@ int launch_backward(const float* z, const float* E, const int64_t* idx, const in
   int32_t* total = reinterpret_cast<int32_t*>(p); p += 256;
   int2* slots = reinterpret_cast<int2*>(p);
 
-  ProfScope* bucket_scope = new ProfScope(KVQ_PROF_BWD_BUCKET, st);
-  struct ScopeGuard { ProfScope*& p; ~ScopeGuard() { delete p; } } bucket_guard{bucket_scope};
-  KVQ_CUDA(cudaMemsetAsync(dE, 0, (size_t)K * D * sizeof(float), st));
-  scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(hist, K, block_sums);
-  KVQ_LAUNCH_CHECK();
-  scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
-  KVQ_LAUNCH_CHECK();
-  scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(hist, K, block_sums, offsets, cursor);
-  KVQ_LAUNCH_CHECK();
-  bucket_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(idx, N, K, k_offset, cursor, slots);
-  KVQ_LAUNCH_CHECK();
-  delete bucket_scope;
-  bucket_scope = nullptr;
+  {
+    ProfScope bucket_scope(KVQ_PROF_BWD_BUCKET, st);
+    KVQ_CUDA(cudaMemsetAsync(dE, 0, (size_t)K * D * sizeof(float), st));
+    scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(hist, K, block_sums);
+    KVQ_LAUNCH_CHECK();
+    scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
+    KVQ_LAUNCH_CHECK();
+    scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(hist, K, block_sums, offsets, cursor);
+    KVQ_LAUNCH_CHECK();
+    bucket_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(idx, N, K, k_offset, cursor, slots);
+    KVQ_LAUNCH_CHECK();
+  }
   ProfScope seg_scope(KVQ_PROF_BWD_SEGMENTED, st);
   const int64_t warps = (N + 31) / 32;
   const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);

@@ -19,8 +19,10 @@
 // Warp roles (320 threads):  warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane of
 // the leader CTA), warps 2..9 = epilogue.  The accumulator is double buffered in TMEM (2 x 256 columns = all
 // 512), so the argmin epilogue of code tile j overlaps the MMAs of tile j+1.  Epilogue warp w reads TMEM lanes
-// 32*(w%4).. (its hardware lane quarter) and one half of the 256 columns; each thread owns one latent row and
-// keeps four independent running (min, index) chains.
+// 32*(w%4).. (its hardware lane quarter) and one half of the 256 columns; each thread owns one latent row: per batch
+// of 32 columns it forms the scores, reduces them with an FMNMX3 tree and looks for the index only when the running
+// minimum improved (TOP2 instantiation: also keeps the runner-up for the exact re-evaluation pass).  TMEM loads run
+// one batch ahead of the reduction, and the accumulator is handed back to the MMA before the last batch is reduced.
 //
 // Barrier protocol (mbarriers in shared memory, same offsets in both CTAs of a pair):
 //   full[s]      leader only   1 arrival (leader producer, expect_tx of BOTH CTAs' bytes) + TMA complete_tx
