@@ -150,6 +150,18 @@ int kvq_backward(const float* z, const float* E, const int64_t* idx, const int32
                  float beta, int64_t n_global, float* dz, float* dE,
                  void* workspace, size_t workspace_bytes, kvq_stream_t stream);
 
+/* Backward of the batch-sharded layer with the all-reduce of the codebook gradient FUSED into the scatter-add kernel.
+ * The dE buffer (K*D floats) is symmetric memory, zeroed on every rank before a cross-rank barrier.  Each bucket sum
+ * is added straight into every rank's replica: with `dE_multicast` (the NVLS multicast address of the buffer) one
+ * `multimem.red.add.v4.f32` per 16 bytes lets the NVSwitch perform the reduction and the broadcast; without it the
+ * kernel issues one system-scope `red.add.v4.f32` per peer.  `dE_peers` is a HOST array of the n_peers unicast
+ * addresses (this rank's own included).  After a second barrier every replica holds the gradient of the global batch.
+ * dz is local as in kvq_backward. */
+int kvq_backward_peers(const float* z, const float* E, const int64_t* idx, const int32_t* hist, const float* g_zq,
+                       const float* g_loss, int64_t N, int D, int64_t K, float beta, int64_t n_global, float* dz,
+                       float* dE_multicast, float* const* dE_peers, int n_peers, int my_rank,
+                       void* workspace, size_t workspace_bytes, kvq_stream_t stream);
+
 /* dz from an assembled z_q (K-sharded codebook, where the winning codebook rows live on other ranks):
  *   dz = g_zq + g_loss * 2 (z - z_q) / (n_global D).   Same autograd term as kvq_backward's dz. */
 int kvq_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t N, int D,

@@ -39,6 +39,8 @@ SIGNATURES = {
     "kvq_forward": (c_int, [_P, _P, c_int64, c_int, c_int64, c_float, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "kvq_backward": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_int64, c_float, c_int64, _P, _P,
                              _P, c_size_t, _P]),
+    "kvq_backward_peers": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_float, c_int64, _P, _P, _P, c_int,
+                                   c_int, _P, c_size_t, _P]),
     "kvq_dz_from_zq": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int64, _P, _P]),
     "kvq_histogram": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),
     "kvq_cooccurrence": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P]),

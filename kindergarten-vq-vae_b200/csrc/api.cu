@@ -310,6 +310,27 @@ int kvq_backward(const float* z, const float* E, const int64_t* idx, const int32
                          (cudaStream_t)stream);
 }
 
+int kvq_backward_peers(const float* z, const float* E, const int64_t* idx, const int32_t* hist, const float* g_zq,
+                       const float* g_loss, int64_t N, int D, int64_t K, float beta, int64_t n_global, float* dz,
+                       float* dE_multicast, float* const* dE_peers, int n_peers, int my_rank, void* ws, size_t ws_bytes,
+                       kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  rc = check_shape("kvq_backward_peers", N, D, K); if (rc) return rc;
+  KVQ_REQUIRE(z && E && idx && hist && ws && dE_peers, KVQ_ERR_ARG, "kvq_backward_peers: null pointer");
+  KVQ_REQUIRE(n_peers >= 1 && n_peers <= MAX_PEERS && my_rank >= 0 && my_rank < n_peers, KVQ_ERR_ARG,
+              "kvq_backward_peers: n_peers must be 1..%d and my_rank inside it", MAX_PEERS);
+  KVQ_REQUIRE(n_global >= N && n_global > 0, KVQ_ERR_ARG, "kvq_backward_peers: n_global must be >= N");
+  KVQ_REQUIRE(((uintptr_t)ws & 255) == 0, KVQ_ERR_WORKSPACE, "kvq_backward_peers: workspace must be 256-byte aligned");
+  RemoteGrad rg;
+  rg.mc = dE_multicast;
+  for (int g = 0; g < MAX_PEERS; ++g) rg.p[g] = g < n_peers ? dE_peers[g] : nullptr;
+  for (int g = 0; g < n_peers; ++g) KVQ_REQUIRE(rg.p[g], KVQ_ERR_ARG, "kvq_backward_peers: peer %d buffer is null", g);
+  rg.n = n_peers;
+  rg.first = (my_rank + 1) % n_peers;
+  return launch_backward(z, E, idx, hist, g_zq, g_loss, N, D, K, 0, beta, n_global, dz, rg.p[my_rank], ws, ws_bytes,
+                         (cudaStream_t)stream, &rg);
+}
+
 int kvq_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t N, int D,
                    int64_t n_global, float* dz, kvq_stream_t stream) {
   int rc = check_device(); if (rc) return rc;

@@ -139,10 +139,44 @@ __global__ void __launch_bounds__(256) bucket_fill_kernel(const int64_t* __restr
 }
 
 // ---- 3. segmented pass -----------------------------------------------------------------------------
+// 128-bit reductions into remote memory: one multimem.red into the NVSwitch multicast address (the switch adds the
+// vector into every GPU's replica), or one system-scope red per peer when multicast is not available.
+__device__ __forceinline__ void red_add_multicast(float4* mc_addr, const float4& v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add_sys(float4* addr, const float4& v) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 template <int VPL, bool MEAN = false>
 __device__ __forceinline__ void flush_bucket(float4 (&acc)[VPL], int code, int p0, int p1, float c2,
                                              const int32_t* __restrict__ offsets, int32_t total, int64_t K,
-                                             float* __restrict__ dE, int D, int lane) {
+                                             float* __restrict__ dE, int D, int lane, const RemoteGrad* remote = nullptr) {
+  if (!MEAN && remote && remote->n > 0) {
+    // fused all-reduce: this rank's bucket sum goes straight into every rank's dE (pre-zeroed symmetric buffer)
+    const int nvec = D >> 2;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = lane + v * 32;
+      if (col < nvec) {
+        const float4 g = make_float4(c2 * acc[v].x, c2 * acc[v].y, c2 * acc[v].z, c2 * acc[v].w);
+        const int64_t off = (int64_t)code * nvec + col;
+        if (remote->mc) {
+          red_add_multicast(reinterpret_cast<float4*>(remote->mc) + off, g);
+        } else {
+          for (int r = 0; r < remote->n; ++r) {
+            int t = remote->first + r;
+            if (t >= remote->n) t -= remote->n;
+            red_add_sys(reinterpret_cast<float4*>(remote->p[t]) + off, g);
+          }
+        }
+      }
+      acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
   const int nvec = D >> 2;
   const int seg_lo = offsets[code];
   const int seg_hi = (code + 1 < K) ? offsets[code + 1] : total;
@@ -166,7 +200,7 @@ __global__ void __launch_bounds__(256) segmented_backward_kernel(
     const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ g_zq,
     const float* __restrict__ g_loss, const int2* __restrict__ slots, const int32_t* __restrict__ offsets,
     const int32_t* __restrict__ total_p, int D, int64_t K, float beta, double inv_nd, float* __restrict__ dz,
-    float* __restrict__ dE) {
+    float* __restrict__ dE, const RemoteGrad remote) {
   constexpr int R = (VPL <= 2) ? 4 : ((VPL <= 4) ? 2 : 1);  // rows in flight, bounded by registers
   const int lane = threadIdx.x & 31;
   const int32_t total = *total_p;
@@ -213,7 +247,7 @@ __global__ void __launch_bounds__(256) segmented_backward_kernel(
     for (int r = 0; r < R; ++r) {
       if ((r0 + r) >= count) break;
       if (codes[r] != cur) {  // warp-uniform: the code is broadcast
-        if (cur >= 0 && dE) flush_bucket<VPL>(acc, cur, p0, p1, c2, offsets, total, K, dE, D, lane);
+        if (cur >= 0 && dE) flush_bucket<VPL>(acc, cur, p0, p1, c2, offsets, total, K, dE, D, lane, &remote);
         cur = codes[r];
         const float4* er = reinterpret_cast<const float4*>(E + (int64_t)cur * D);
 #pragma unroll
@@ -241,7 +275,7 @@ __global__ void __launch_bounds__(256) segmented_backward_kernel(
       }
     }
   }
-  if (cur >= 0 && dE) flush_bucket<VPL>(acc, cur, p0, p1, c2, offsets, total, K, dE, D, lane);
+  if (cur >= 0 && dE) flush_bucket<VPL>(acc, cur, p0, p1, c2, offsets, total, K, dE, D, lane, &remote);
 }
 
 // k-means centroid update on the same bucketed layout: centroid[k] = mean of the latents assigned to k.
@@ -427,8 +461,12 @@ size_t backward_workspace_bytes(int64_t N, int64_t K) {
 
 int launch_backward(const float* z, const float* E, const int64_t* idx, const int32_t* hist, const float* g_zq,
                     const float* g_loss, int64_t N, int D, int64_t K, int64_t k_offset, float beta,
-                    int64_t n_global, float* dz, float* dE, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    int64_t n_global, float* dz, float* dE, void* ws, size_t ws_bytes, cudaStream_t st,
+                    const RemoteGrad* remote) {
+  RemoteGrad rg;
+  if (remote) rg = *remote; else { rg.mc = nullptr; rg.n = 0; rg.first = 0; }
   if (N <= 0) {
+    if (rg.n > 0) return KVQ_OK;   // remote mode: the caller zeroed the symmetric buffer, nothing to add
     if (dE && K > 0) KVQ_CUDA(cudaMemsetAsync(dE, 0, (size_t)K * D * sizeof(float), st));
     return KVQ_OK;
   }
@@ -463,7 +501,8 @@ int launch_backward(const float* z, const float* E, const int64_t* idx, const in
 
   {
     ProfScope bucket_scope(KVQ_PROF_BWD_BUCKET, st);
-    KVQ_CUDA(cudaMemsetAsync(dE, 0, (size_t)K * D * sizeof(float), st));
+    // remote mode: the symmetric dE buffer was zeroed by the caller on every rank before the cross-rank barrier
+    if (rg.n == 0) KVQ_CUDA(cudaMemsetAsync(dE, 0, (size_t)K * D * sizeof(float), st));
     scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(hist, K, block_sums);
     KVQ_LAUNCH_CHECK();
     scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
@@ -479,7 +518,7 @@ int launch_backward(const float* z, const float* E, const int64_t* idx, const in
 #define KVQ_SEG(V)                                                                                              \
   case V:                                                                                                       \
     segmented_backward_kernel<V><<<blocks, wpb * 32, 0, st>>>(z, E, g_zq, g_loss, slots, offsets, total, D, K,   \
-                                                              beta, inv_nd, dz, dE);                            \
+                                                              beta, inv_nd, dz, dE, rg);                        \
     break;
   switch (vpl) { KVQ_SEG(1) KVQ_SEG(2) KVQ_SEG(3) KVQ_SEG(4) KVQ_SEG(5) KVQ_SEG(6) KVQ_SEG(7) KVQ_SEG(8) }
 #undef KVQ_SEG

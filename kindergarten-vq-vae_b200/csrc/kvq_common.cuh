@@ -106,6 +106,13 @@ struct ShardPtrs {           // codebook shards of every rank: global code c liv
   int64_t k_per;
 };
 
+struct RemoteGrad {          // batch-sharded backward: where the bucket sums of dE are accumulated
+  float* mc;                 // multicast (NVLS) address of the symmetric dE buffer, or null
+  float* p[MAX_PEERS];       // unicast peer addresses of the same buffer (used when mc is null)
+  int n;                     // 0 = local dE (single GPU / NCCL all-reduce afterwards)
+  int first;
+};
+
 // ---- kernels' host launchers (one per translation unit) --------------------------------------------
 int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st);
 int launch_search_fp32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
@@ -131,7 +138,8 @@ int launch_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global,
                     float* loss, float* perplexity, cudaStream_t st);
 int launch_backward(const float* z, const float* E, const int64_t* idx, const int32_t* hist, const float* g_zq,
                     const float* g_loss, int64_t N, int D, int64_t K, int64_t k_offset, float beta,
-                    int64_t n_global, float* dz, float* dE, void* ws, size_t ws_bytes, cudaStream_t st);
+                    int64_t n_global, float* dz, float* dE, void* ws, size_t ws_bytes, cudaStream_t st,
+                    const RemoteGrad* remote = nullptr);
 size_t backward_workspace_bytes(int64_t N, int64_t K);
 int launch_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t numel,
                       double inv_nd, float* dz, cudaStream_t st);

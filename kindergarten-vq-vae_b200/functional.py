@@ -279,3 +279,27 @@ def quantize_shards(z: torch.Tensor, shard_ptrs, k_per: int, idx: torch.Tensor, 
                                               z_q.data_ptr(), sq_sum.data_ptr(), hist.data_ptr(), _stream()),
               "kvq_quantize_shards")
     return z_q, sq_sum, hist
+
+
+def vq_backward_peers(z: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, hist: torch.Tensor, beta: float, *,
+                      g_zq: Optional[torch.Tensor], g_loss: torch.Tensor, need_dz: bool, n_global: int,
+                      dE_peer_ptrs, dE_multicast_ptr: int, my_rank: int, ws: Optional[torch.Tensor] = None):
+    """Batch-sharded backward whose codebook-gradient all-reduce is fused into the scatter-add kernel (multimem.red
+    through the NVSwitch, or per-peer red).  The symmetric dE buffer must be zero on every rank.  Returns dz or None."""
+    import ctypes
+    _req(z, "z", torch.float32); _req(E, "E", torch.float32); _req(idx, "idx", torch.int64); _req(hist, "hist", torch.int32)
+    _req(g_loss, "g_loss", torch.float32)
+    if g_zq is not None:
+        _req(g_zq, "g_zq", torch.float32)
+    N, D = z.shape
+    K = E.shape[0]
+    dz = torch.empty_like(z) if need_dz else None
+    if ws is None:
+        ws = workspace(N, D, K, z.device)
+    arr = (ctypes.c_void_p * len(dE_peer_ptrs))(*[int(p) for p in dE_peer_ptrs])
+    with torch.cuda.device(z.device):
+        check(_lib.load().kvq_backward_peers(z.data_ptr(), E.data_ptr(), idx.data_ptr(), hist.data_ptr(), _ptr(g_zq),
+                                             g_loss.data_ptr(), N, D, K, float(beta), n_global, _ptr(dz),
+                                             int(dE_multicast_ptr) if dE_multicast_ptr else None, arr, len(dE_peer_ptrs),
+                                             my_rank, ws.data_ptr(), ws.numel(), _stream()), "kvq_backward_peers")
+    return dz

@@ -50,9 +50,20 @@ def shard_bounds(total: int, parts: int, part: int):
 # ------------------------------------------------------------------------------------------------
 # batch-sharded (data parallel)
 # ------------------------------------------------------------------------------------------------
+class _GradPeerMemory:
+    """Symmetric (peer-mapped, multicast-capable where the fabric allows) buffer for the codebook gradient."""
+
+    def __init__(self, group, K: int, D: int, device):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.buf = symm.empty(K, D, dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+
+
 class _BatchShardedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, E, beta, mode, group, n_global, backend):
+    def forward(ctx, z, E, beta, mode, group, n_global, backend, grad_peer=None):
         N, D = z.shape
         idx, _ = backend.search(z, E, mode=mode)
         z_q, sq_sum, hist_local = backend.quantize(z, E, idx)
@@ -64,7 +75,7 @@ class _BatchShardedFn(torch.autograd.Function):
         loss, perplexity = backend.finalize(sq_sum, hist, n_global, D, beta)
         loss, perplexity = loss.clone(), perplexity.clone()
         ctx.save_for_backward(z, E, idx, hist_local)
-        ctx.beta, ctx.group, ctx.n_global, ctx.backend = beta, group, n_global, backend
+        ctx.beta, ctx.group, ctx.n_global, ctx.backend, ctx.grad_peer = beta, group, n_global, backend, grad_peer
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(perplexity, idx, hist)
         return loss, z_q, perplexity, idx, hist
@@ -75,6 +86,18 @@ class _BatchShardedFn(torch.autograd.Function):
         need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if g_zq is not None:
             g_zq = g_zq.contiguous()
+        gp = ctx.grad_peer
+        if gp is not None and need_dE and _world(ctx.group) > 1:
+            # fused exchange: the scatter-add kernel reduces its bucket sums into every rank's dE over NVLink / NVSwitch
+            gl = (torch.zeros((), device=z.device) if g_loss is None
+                  else g_loss.detach().to(torch.float32).contiguous())
+            gp.buf.zero_()
+            gp.handle.barrier(channel=0)                  # every replica is zero before any remote reduction lands
+            dz = _cuda_backend.vq_backward_peers(z, E, idx, hist_local, ctx.beta, g_zq=g_zq, g_loss=gl, need_dz=need_dz,
+                                                 n_global=ctx.n_global, dE_peer_ptrs=gp.handle.buffer_ptrs,
+                                                 dE_multicast_ptr=gp.multicast_ptr, my_rank=_rank(ctx.group))
+            gp.handle.barrier(channel=1)                  # all ranks' reductions are complete
+            return dz, gp.buf.clone(), None, None, None, None, None, None
         if g_loss is None:
             dz = g_zq if need_dz else None
             dE = torch.zeros_like(E) if need_dE else None
@@ -84,7 +107,7 @@ class _BatchShardedFn(torch.autograd.Function):
                                              need_dz=need_dz, need_dE=need_dE, n_global=ctx.n_global)
         if need_dE and _world(ctx.group) > 1:
             dist.all_reduce(dE, op=dist.ReduceOp.SUM, group=ctx.group)   # codebook gradient of the global batch
-        return dz, dE, None, None, None, None, None
+        return dz, dE, None, None, None, None, None, None
 
 
 class BatchShardedVectorQuantizer(nn.Module):
@@ -93,10 +116,17 @@ class BatchShardedVectorQuantizer(nn.Module):
     gradient is all-reduced here -- do not also wrap `embedding.weight` in DistributedDataParallel."""
 
     def __init__(self, n_e, e_dim, beta, vq_codebook_init_values: Tensor = None, *, process_group=None,
-                 search: str = "auto", min_encodings=False, backend=None):
+                 search: str = "auto", min_encodings=False, backend=None, exchange: str = "nccl"):
+        """exchange="nccl": all-reduce(SUM) of dE after the backward kernel.  exchange="nvlink": the all-reduce is fused
+        into the scatter-add kernel (multimem.red through the NVSwitch when the symmetric buffer has a multicast
+        address, else one system-scope red per peer); needs torch symmetric memory, world <= 8."""
         super().__init__()
         self.n_e, self.e_dim, self.beta = n_e, e_dim, beta
         self.search, self.group = search, process_group
+        if exchange not in ("nccl", "nvlink"):
+            raise ValueError("exchange must be 'nccl' or 'nvlink'")
+        self.exchange = exchange
+        self._grad_peer = None
         self.return_min_encodings = min_encodings
         self.backend = backend if backend is not None else _cuda_backend
         self.embedding = nn.Embedding(n_e, e_dim)
@@ -111,8 +141,11 @@ class BatchShardedVectorQuantizer(nn.Module):
         zf = z.view((-1, self.e_dim))
         if n_global is None:
             n_global = zf.shape[0] * _world(self.group)
+        if self.exchange == "nvlink" and _world(self.group) > 1 and self._grad_peer is None:
+            self._grad_peer = _GradPeerMemory(self.group, self.n_e, self.e_dim, z.device)
         loss, z_q, perplexity, idx, _ = _BatchShardedFn.apply(zf, self.embedding.weight, float(self.beta),
-                                                               self.search, self.group, int(n_global), self.backend)
+                                                               self.search, self.group, int(n_global), self.backend,
+                                                               self._grad_peer)
         want = self.return_min_encodings
         if want == "auto":
             want = zf.shape[0] * self.n_e * 4 <= ONEHOT_AUTO_BYTES

@@ -32,22 +32,31 @@ def main():
         l0, q0, p0, _, i0 = ref.forward(zr, dev)
         (l0 * w + (q0 * gz.to(dev)).sum()).backward()
 
-        # ---- batch-sharded ----
-        vq = kvq.BatchShardedVectorQuantizer(K, D, beta, vq_codebook_init_values=E, search=search).to(dev)
+        # ---- batch-sharded: NCCL all-reduce of dE, then the all-reduce fused into the scatter-add kernel ----
         lo, hi = rank * B // world, (rank + 1) * B // world
-        zl = z[lo:hi].to(dev).requires_grad_(True)
-        l1, q1, p1, _, i1 = vq.forward(zl, dev)
-        (l1 * w + (q1 * gz[lo:hi].to(dev)).sum()).backward()
-        same = (i1 == i0[lo:hi]).reshape(-1)
-        frac = float(same.float().mean())
-        assert frac > 0.999, f"batch-sharded idx agreement {frac}"     # split searches may flip exact near-ties
-        assert torch.equal(q1.detach().reshape(-1, D)[same], q0.detach()[lo:hi].reshape(-1, D)[same])
-        if frac == 1.0:
-            assert abs(float(l1) - float(l0)) <= 1e-5 * float(l0), (float(l1), float(l0))
-            assert abs(float(p1) - float(p0)) <= 1e-5 * float(p0)
-            assert torch.allclose(zl.grad, zr.grad[lo:hi], rtol=1e-5, atol=1e-7)
-            dE = vq.embedding.weight.grad
-            assert float((dE - ref.embedding.weight.grad).abs().max()) <= 2e-5 * float(ref.embedding.weight.grad.abs().max())
+        for exchange in ("nccl", "nvlink"):
+            vq = kvq.BatchShardedVectorQuantizer(K, D, beta, vq_codebook_init_values=E, search=search,
+                                                 exchange=exchange).to(dev)
+            for rep in range(2):            # twice: the symmetric gradient buffer is reused across steps
+                vq.zero_grad()
+                zl = z[lo:hi].to(dev).requires_grad_(True)
+                l1, q1, p1, _, i1 = vq.forward(zl, dev)
+                (l1 * w + (q1 * gz[lo:hi].to(dev)).sum()).backward()
+            same = (i1 == i0[lo:hi]).reshape(-1)
+            frac = float(same.float().mean())
+            assert frac > 0.999, f"batch-sharded[{exchange}] idx agreement {frac}"     # split searches may flip exact near-ties
+            assert torch.equal(q1.detach().reshape(-1, D)[same], q0.detach()[lo:hi].reshape(-1, D)[same])
+            fr = torch.tensor([frac], device=dev); dist.all_reduce(fr, op=dist.ReduceOp.MIN)
+            if float(fr) == 1.0:
+                assert abs(float(l1) - float(l0)) <= 1e-5 * float(l0), (float(l1), float(l0))
+                assert abs(float(p1) - float(p0)) <= 1e-5 * float(p0)
+                assert torch.allclose(zl.grad, zr.grad[lo:hi], rtol=1e-5, atol=1e-7)
+                dE = vq.embedding.weight.grad
+                err = float((dE - ref.embedding.weight.grad).abs().max()); scale = float(ref.embedding.weight.grad.abs().max())
+                assert err <= 2e-5 * scale, (exchange, err, scale)
+            if rank == 0:
+                mc = vq._grad_peer.multicast_ptr if vq._grad_peer is not None else None
+                print(f"  batch-sharded exchange={exchange}: idx agreement {frac:.6f} multicast_ptr={mc}", flush=True)
 
         # ---- codebook-sharded: NCCL exchange, then the fused NVLink peer-memory exchange ----
         for exchange in ("nccl", "nvlink"):

@@ -135,12 +135,13 @@ def multi():
 
     # ---- C5: batch-sharded, K = 65536, weak (N = G * 2^20) and strong (N = 2^20) scaling ----
     K = 65536
-    for mode, n_local in (("weak", 1 << 20), ("strong", (1 << 20) // world)):
+    for mode, n_local, exchange in (("weak", 1 << 20, "nccl"), ("strong", (1 << 20) // world, "nccl"),
+                                    ("weak", 1 << 20, "nvlink"), ("strong", (1 << 20) // world, "nvlink")):
         g = torch.Generator(device=dev).manual_seed(69 + rank)
         z = torch.randn(n_local, D, device=dev, generator=g); gz = torch.randn(n_local, D, device=dev, generator=g)
         ge = torch.Generator(device=dev).manual_seed(7)
         E = torch.randn(K, D, device=dev, generator=ge)
-        vq = kvq.BatchShardedVectorQuantizer(K, D, BETA, vq_codebook_init_values=E, search="tf32").to(dev)
+        vq = kvq.BatchShardedVectorQuantizer(K, D, BETA, vq_codebook_init_values=E, search="tf32", exchange=exchange).to(dev)
         z3 = z.view(n_local // 64, 64, D).requires_grad_(True); g3 = gz.view_as(z3)
 
         def step():
@@ -151,7 +152,7 @@ def multi():
         t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
             ms = float(t)
-            print(json.dumps(dict(config=f"C5-dp-{mode}", gpus=world, N_total=n_local * world, D=D, K=K, ms_fwd_bwd=ms,
+            print(json.dumps(dict(config=f"C5-dp-{mode}", exchange=exchange, gpus=world, N_total=n_local * world, D=D, K=K, ms_fwd_bwd=ms,
                                   latents_per_s=n_local * world / ms * 1e3)), flush=True)
         del vq, z, gz, E, z3, g3
         torch.cuda.empty_cache()
