@@ -78,3 +78,47 @@ def test_module_refuses_cpu_tensors():
         seq_acc(torch.zeros(2, 3, dtype=torch.long), torch.zeros(2, 3, dtype=torch.long))
     with pytest.raises(RuntimeError):
         replace_pct_rand_values(torch.zeros(2, 3, dtype=torch.long), 0.5, 0, 10)
+
+
+def test_header_is_plain_c_and_a_c_host_links(lib, tmp_path):
+    """include/kvq.h compiles as C99 and a C program links against libkvq.so with nothing but the header."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "kvq.h"
+int main(void) {
+  size_t ws = kvq_workspace_bytes(1 << 20, 256, 65536);
+  long long key_lo = kvq_pack_key(-1.0f, 7u), key_hi = kvq_pack_key(2.0f, 0u);
+  int rc = kvq_forward(NULL, NULL, 16, 32, 8, 0.25f, KVQ_SEARCH_AUTO, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL);
+  printf("%d %zu %d %d\n", kvq_version(), ws, key_lo < key_hi, rc != KVQ_OK);
+  return 0;
+}
+''')
+    pkg = os.path.join(ROOT, "kindergarten-vq-vae_b200")
+    exe = tmp_path / "host"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", pkg, "-l:libkvq.so", f"-Wl,-rpath,{pkg}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "100" and int(out[1]) > 0 and out[2] == "1" and out[3] == "1"
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU, oracle port) emits one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "latents/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("VQ latents/sec (fwd+bwd) at K=65536,D=256")
+    for key in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config",
+                "cpu_baseline", "e2e"):
+        assert key in line
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["value"] > 0
