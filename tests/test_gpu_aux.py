@@ -95,6 +95,28 @@ def test_host_end_to_end_matches_device_path():
     F._lib.load().kvq_host_release()
 
 
+@pytest.mark.parametrize("N,D,K,mode", [(700, 768, 512, "auto"), (1500, 96, 40, "fp32"), (260, 36, 9, "auto")])
+def test_host_end_to_end_other_shapes(N, D, K, mode):
+    """Host-buffer entry point on BERT-width latents (streaming-operand search), on a D the tensor-core kernel does
+    not take, with a ragged last chunk -- against the oracle."""
+    k = _kvq()
+    F = k.functional
+    gen = torch.Generator().manual_seed(21)
+    z = torch.randn(N, D, generator=gen); E = torch.randn(K, D, generator=gen); g = torch.randn(N, D, generator=gen)
+    out = F.forward_backward_host(z, E, g, 0.5, 0.25, mode=mode, rows_per_chunk=256)
+    ref = O.forward_fp32(z, E, 0.25)
+    par = O.index_parity(out["idx"], ref.idx, z, E, exact_fp32=(mode == "fp32"))
+    assert par.unexcused == 0
+    if par.raw_mismatch == 0:
+        dz, dE = O.backward_closed_form(z, E, ref.idx, 0.25, g_zq=g, g_loss=0.5)
+        assert torch.equal(out["z_q"], ref.z_q.view(N, D))
+        assert abs(float(out["loss"]) - float(ref.loss)) <= 2e-5 * float(ref.loss)
+        assert abs(float(out["perplexity"]) - float(ref.perplexity)) <= 2e-5 * float(ref.perplexity)
+        assert torch.allclose(out["dz"], dz.float(), rtol=1e-5, atol=1e-7)
+        assert (out["dE"] - dE.float()).abs().max() <= 1e-5 * dE.abs().max()
+    F._lib.load().kvq_host_release()
+
+
 def test_kmeans2_matches_scipy_given_the_same_initial_centroids():
     """Device Lloyd iterations vs scipy.cluster.vq.kmeans2 (the call of vq_codebook_init_weights.py:85)."""
     from scipy.cluster.vq import kmeans2 as sp_kmeans2

@@ -66,7 +66,7 @@ def check_against(out, ref, z, E, search, expect_exact_idx=False):
     return par
 
 
-@pytest.mark.parametrize("search", ["fp32", "tf32"])
+@pytest.mark.parametrize("search", ["fp32", "tf32", "auto"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_golden_vectors(name, search):
     g = load_golden(name)
@@ -119,7 +119,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("search", ["fp32", "tf32"])
+@pytest.mark.parametrize("search", ["fp32", "tf32", "auto"])
 @pytest.mark.parametrize("B,S,D,K,init", SHAPES)
 def test_oracle_parity_shapes(B, S, D, K, init, search):
     z, E, gz = _seeded(B, S, D, K, init)
