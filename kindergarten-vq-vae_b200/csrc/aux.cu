@@ -1,6 +1,7 @@
 // (1) token-id corruption helpers (common/tensor_utils.py:13-49, :52-87) with a counter-based device RNG;
 // (2) the host-buffer end-to-end entry point: row-chunked H2D / compute / D2H pipeline on three streams.
 #include <mutex>
+#include <vector>
 
 #include "kvq_common.cuh"
 
@@ -161,7 +162,24 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
               "kvq_forward_backward_host: bad shape N=%lld D=%d K=%lld", (long long)N, D, (long long)K);
   if (rows_per_chunk <= 0) rows_per_chunk = 131072;
   rows_per_chunk = (rows_per_chunk + 127) / 128 * 128;
-  const int64_t chunks = (N + rows_per_chunk - 1) / rows_per_chunk;
+  // Chunk boundaries.  The pipeline's exposed time is the first chunk's host->device copy (compute cannot start
+  // before it) plus the last chunk's device->host copy, so when the batch is large the first and the last chunk are
+  // shrunk to one full wave of the search kernel (one 256-latent tile per CTA pair); the middle stays coarse.
+  std::vector<int64_t> bounds;
+  {
+    const int64_t wave = (int64_t)(sm_count() / 2) * 256;
+    bounds.push_back(0);
+    if (wave >= 128 && rows_per_chunk > wave && N >= 2 * wave + rows_per_chunk) {
+      bounds.push_back(wave);
+      while (bounds.back() + rows_per_chunk < N - wave) bounds.push_back(bounds.back() + rows_per_chunk);
+      if (bounds.back() < N - wave) bounds.push_back(N - wave);
+      bounds.push_back(N);
+    } else {
+      while (bounds.back() + rows_per_chunk < N) bounds.push_back(bounds.back() + rows_per_chunk);
+      bounds.push_back(N);
+    }
+  }
+  const int64_t chunks = (int64_t)bounds.size() - 1;
   KVQ_REQUIRE(chunks <= 4096, KVQ_ERR_ARG, "kvq_forward_backward_host: too many chunks (%lld)", (long long)chunks);
 
   std::lock_guard<std::mutex> lock(g_pipe.mu);
@@ -206,7 +224,7 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   KVQ_TRYC(cudaMemcpyAsync(hp.scal + 2, &g_loss_h, 4, cudaMemcpyHostToDevice, hp.s_in));
   KVQ_TRYC(cudaEventRecord(ev_E, hp.s_in));
   for (int64_t c = 0; c < chunks && status == KVQ_OK; ++c) {
-    const int64_t r0 = c * rows_per_chunk, rows = (N - r0 < rows_per_chunk) ? (N - r0) : rows_per_chunk;
+    const int64_t r0 = bounds[c], rows = bounds[c + 1] - bounds[c];
     KVQ_TRYC(cudaMemcpyAsync(hp.z + r0 * D, z_h + r0 * D, (size_t)rows * D * 4, cudaMemcpyHostToDevice, hp.s_in));
     KVQ_TRYC(cudaMemcpyAsync(hp.g + r0 * D, g_h + r0 * D, (size_t)rows * D * 4, cudaMemcpyHostToDevice, hp.s_in));
     KVQ_TRYC(cudaEventRecord(ev_in[c], hp.s_in));
@@ -217,7 +235,7 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   KVQ_TRYC(cudaMemsetAsync(sq_sum, 0, sizeof(double), hp.s_cmp));
   KVQ_TRYC(cudaMemsetAsync(hist, 0, (size_t)K * 4, hp.s_cmp));
   for (int64_t c = 0; c < chunks && status == KVQ_OK; ++c) {
-    const int64_t r0 = c * rows_per_chunk, rows = (N - r0 < rows_per_chunk) ? (N - r0) : rows_per_chunk;
+    const int64_t r0 = bounds[c], rows = bounds[c + 1] - bounds[c];
     KVQ_TRYC(cudaStreamWaitEvent(hp.s_cmp, ev_in[c], 0));
     KVQ_TRY(run_search(m, hp.z + r0 * D, hp.E, e2, rows, D, K, hp.idx + r0, keys + r0, hp.s_cmp));
     KVQ_TRY(launch_quantize(hp.z + r0 * D, hp.E, hp.idx + r0, rows, D, K, 0, 0, hp.zq + r0 * D, sq_sum, hist, hp.s_cmp));
