@@ -331,3 +331,33 @@ def test_tf32_refine_search_equals_exact_argmin(N, D, K, init):
     vq = k.VectorQuantizer(K, D, 0.25, vq_codebook_init_values=E, search="tf32_refine", min_encodings=False).to(DEV)
     loss, z_q, perp, _, idx = vq.forward(z.view(N // 16, 16, D), DEV)
     assert torch.equal(idx.view(-1), refined) and torch.equal(z_q.view(N, D), z + (E[refined] - z))
+
+
+def test_peer_entry_points_with_a_single_peer():
+    """kvq_search_peers / kvq_quantize_shards / kvq_backward_peers (the fused NVLink exchanges) with a peer table that
+    holds only this GPU's own buffers: same kernels and code paths as the multi-GPU runs, checkable on one device."""
+    F = _kvq().functional
+    z, E, gz = _seeded(3, 211, 128, 777, "normal", seed=9)
+    zf, Ed, gd = z.view(-1, 128).to(DEV), E.to(DEV), gz.view(-1, 128).to(DEV)
+    N, D, K = zf.shape[0], 128, 777
+    for mode in ("tf32", "fp32"):
+        ref_idx, _ = F.search(zf, Ed, mode=mode)
+        keys = torch.full((N,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=DEV)
+        F.search_peers(zf, Ed, [keys.data_ptr()], 0, mode=mode)
+        assert torch.equal(F.keys_to_idx(keys), ref_idx)
+        # two "shards" living on the same device: rows [0, 400) and [400, 777) padded to 400
+        lo = Ed[:400].contiguous()
+        hi = torch.zeros(400, D, device=DEV); hi[:377] = Ed[400:]
+        zq_s, sq_s, hist_s = F.quantize_shards(zf, [lo.data_ptr(), hi.data_ptr()], 400, ref_idx, 800)
+        zq, sq, hist = F.quantize(zf, Ed, ref_idx)
+        assert torch.equal(zq_s, zq) and torch.equal(hist_s[:K], hist) and int(hist_s[K:].sum()) == 0
+        assert abs(float(sq_s) - float(sq)) <= 1e-9 * float(sq)
+        # backward with the reduction "fused" into the scatter-add (single replica, unicast red path)
+        gl = torch.tensor(1.3, device=DEV)
+        dz_ref, dE_ref = F.vq_backward(zf, Ed, ref_idx, hist, 0.25, g_zq=gd, g_loss=gl)
+        dE_buf = torch.zeros(K, D, device=DEV)
+        dz = F.vq_backward_peers(zf, Ed, ref_idx, hist, 0.25, g_zq=gd, g_loss=gl, need_dz=True, n_global=N,
+                                 dE_peer_ptrs=[dE_buf.data_ptr()], dE_multicast_ptr=0, my_rank=0)
+        assert torch.equal(dz, dz_ref)
+        assert float((dE_buf - dE_ref).abs().max()) <= 1e-5 * float(dE_ref.abs().max())
+        assert bool((dE_buf[hist == 0] == 0).all())
