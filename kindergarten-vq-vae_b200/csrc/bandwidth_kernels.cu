@@ -68,32 +68,49 @@ int launch_keys_to_idx(const long long* keys, int64_t N, int64_t* idx, cudaStrea
 __global__ void __launch_bounds__(256) refine_top2_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                           int64_t N, int D, int64_t* __restrict__ idx,
                                                           const int64_t* __restrict__ idx2) {
+  constexpr int R = 4;   // latents per warp, all their loads issued before the first use (memory-level parallelism)
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= N) return;
-  const int64_t a = idx[row], b = idx2[row];
-  if (a == b) return;
-  const float4* zr = reinterpret_cast<const float4*>(z + row * D);
-  const float4* ea = reinterpret_cast<const float4*>(E + a * D);
-  const float4* eb = reinterpret_cast<const float4*>(E + b * D);
-  double da = 0.0, db = 0.0;
-  for (int v = lane; v < (D >> 2); v += 32) {
-    const float4 x = ld_stream(zr + v), p = __ldg(ea + v), q = __ldg(eb + v);
-    double t;
-    t = (double)x.x - (double)p.x; da += t * t;  t = (double)x.y - (double)p.y; da += t * t;
-    t = (double)x.z - (double)p.z; da += t * t;  t = (double)x.w - (double)p.w; da += t * t;
-    t = (double)x.x - (double)q.x; db += t * t;  t = (double)x.y - (double)q.y; db += t * t;
-    t = (double)x.z - (double)q.z; db += t * t;  t = (double)x.w - (double)q.w; db += t * t;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= N) return;
+  int64_t a[R], b[R];
+  double da[R], db[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int64_t row = min(row0 + r, N - 1);       // clamped rows recompute the last latent, harmlessly
+    a[r] = idx[row];
+    b[r] = idx2[row];
+    da[r] = 0.0;
+    db[r] = 0.0;
   }
-  da = warp_sum(da);
-  db = warp_sum(db);
-  if (lane == 0 && (db < da || (db == da && b < a))) idx[row] = b;
+  for (int v = lane; v < (D >> 2); v += 32) {
+    float4 x[R], p[R], q[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = min(row0 + r, N - 1);
+      x[r] = ld_stream(reinterpret_cast<const float4*>(z + row * D) + v);
+      p[r] = __ldg(reinterpret_cast<const float4*>(E + a[r] * D) + v);
+      q[r] = __ldg(reinterpret_cast<const float4*>(E + b[r] * D) + v);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double t;
+      t = (double)x[r].x - (double)p[r].x; da[r] += t * t;  t = (double)x[r].y - (double)p[r].y; da[r] += t * t;
+      t = (double)x[r].z - (double)p[r].z; da[r] += t * t;  t = (double)x[r].w - (double)p[r].w; da[r] += t * t;
+      t = (double)x[r].x - (double)q[r].x; db[r] += t * t;  t = (double)x[r].y - (double)q[r].y; db[r] += t * t;
+      t = (double)x[r].z - (double)q[r].z; db[r] += t * t;  t = (double)x[r].w - (double)q[r].w; db[r] += t * t;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const double sa = warp_sum(da[r]), sb = warp_sum(db[r]);
+    if (lane == 0 && row0 + r < N && a[r] != b[r] && (sb < sa || (sb == sa && b[r] < a[r]))) idx[row0 + r] = b[r];
+  }
 }
 
 int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2, cudaStream_t st) {
   if (N <= 0) return KVQ_OK;
-  const int wpb = 8;
-  refine_top2_kernel<<<(unsigned)((N + wpb - 1) / wpb), wpb * 32, 0, st>>>(z, E, N, D, idx, idx2);
+  const int rows_per_block = 8 * 4;   // 8 warps x 4 latents
+  refine_top2_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(z, E, N, D, idx, idx2);
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }
