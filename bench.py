@@ -295,6 +295,30 @@ def run_kvq(args):
                       "tolerance": "2^-9 * |z_i| * max_k |E_k| on the fp64 squared-distance gap (DESIGN.md section 3)"}
             del d, zs, Ed
 
+    # ---- the default search mode of the module ("auto" = tf32_refine) next to the plain tf32 search that is timed above
+    refine = None
+    if rank == 0:
+        with torch.no_grad():
+            Ew = vq.embedding.weight.detach()
+            times = {}
+            for mode in ("tf32", "tf32_refine"):
+                F.search(z, Ew, mode=mode)
+                torch.cuda.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record()
+                for _ in range(3):
+                    idx_m, _ = F.search(z, Ew, mode=mode)
+                r1.record(); torch.cuda.synchronize()
+                times[mode] = r0.elapsed_time(r1) / 3
+                if mode == "tf32_refine" and parity is not None:
+                    Ed = E.double(); zs = z[rows].double()
+                    best = ((Ed * Ed).sum(1) - 2.0 * zs @ Ed.t()).argmin(1)
+                    times["mismatch"] = int((best != idx_m[rows]).sum())
+                    del Ed, zs
+            refine = {"search_ms_tf32": times["tf32"], "search_ms_tf32_refine": times["tf32_refine"],
+                      "index_mismatch_vs_fp64_tf32_refine": times.get("mismatch"),
+                      "note": "search + code norms only, outside the timed steps; bench steps use search='tf32'"}
+
     # ---- end to end with host buffers (H2D + compute + D2H inside the timed region) --------------------
     e2e = None
     if not args.no_e2e:
@@ -374,7 +398,7 @@ def run_kvq(args):
                        "codebook_init": "data-scale: N(0,1) rows + 0.1 noise"},
             "roofline": roof, "roofline_other_kernels": others, "kernel_ms": prof,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "host_placement": numa, "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp), "index_parity": parity,
+            "host_placement": numa, "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp), "index_parity": parity, "refine_mode": refine,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
