@@ -122,3 +122,24 @@ def test_reference_arm_prints_the_contract_line():
         assert key in line
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["value"] > 0
+
+
+def test_pack_key_order_property(lib):
+    """Signed order of packed keys == lexicographic (score, index) order, for arbitrary finite / infinite floats."""
+    import struct
+    from hypothesis import given, settings, strategies as st
+
+    f32 = st.floats(width=32, allow_nan=False, allow_infinity=True)
+    u32 = st.integers(min_value=0, max_value=0xFFFFFFFF)
+
+    @settings(max_examples=400, deadline=None)
+    @given(f32, u32, f32, u32)
+    def check(s1, i1, s2, i2):
+        k1 = lib.kvq_pack_key(ctypes.c_float(s1), ctypes.c_uint32(i1))
+        k2 = lib.kvq_pack_key(ctypes.c_float(s2), ctypes.c_uint32(i2))
+        a = (struct.unpack("f", struct.pack("f", s1))[0] + 0.0, i1)      # -0.0 folds into +0.0
+        b = (struct.unpack("f", struct.pack("f", s2))[0] + 0.0, i2)
+        assert (k1 < k2) == (a < b) and (k1 == k2) == (a == b)
+        assert k1 & 0xFFFFFFFF == i1
+
+    check()
