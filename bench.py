@@ -35,6 +35,16 @@ K = 65536
 BETA = 0.25
 SEED = 69  # the reference's DS_GEN_SEED (common/consts.py:3)
 CPU_SAMPLE_ROWS = 4096
+PARITY_ROWS = 8192          # rows of the measured batch checked against the oracle's reference-order fp32 argmin
+REF_CUDA_ROWS = 16384       # "same box" bar: the reference's own torch ops on the B200 at the largest N that fits
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the headline shape, from the `ncu --set full` captures
+# under profiles/ (file named per entry); None = not captured for this build.
+NCU_TRAFFIC = {
+    "search": (4.662e9, "profiles/r01/ncu_full_final_kernels.summary.csv"),
+    "quantize": (2.227e9, "profiles/r01/ncu_full_final_kernels.summary.csv"),
+    "bwd_segmented": (3.267e9, "profiles/r01/ncu_full_final_kernels.summary.csv"),
+}
 
 
 def peaks():
@@ -176,6 +186,49 @@ def cpu_reference_rate(torch, steps, warmup, rows):
     return rows / dt, dt, torch.get_num_threads()
 
 
+def reference_on_cuda(torch, dev):
+    """The reference layer's own PyTorch ops (oracle.vq_oracle.LiteralVectorQuantizer = VectorQuantizer.py:55-93 restated,
+    host-built one-hot and all) forward + backward on the GPU, fp32 and with allow_tf32, at the largest N whose dense
+    N x K temporaries fit comfortably.  A reported bar, not part of any timed kvq region."""
+    from oracle import vq_oracle as O
+    rows = REF_CUDA_ROWS
+    gen = torch.Generator(device=dev).manual_seed(SEED)
+    z = torch.randn(rows // 64, 64, D, device=dev, generator=gen).requires_grad_(True)
+    gz = torch.randn(rows // 64, 64, D, device=dev, generator=gen)
+    E = torch.randn(K, D, device=dev, generator=gen)
+    one = torch.ones((), device=dev)
+    out = {"latents_per_step": rows, "K": K, "D": D,
+           "what": "oracle.vq_oracle.LiteralVectorQuantizer (the reference's tensor expressions) on cuda, fwd + bwd"}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, flag in (("fp32", False), ("allow_tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = flag
+            vq = O.LiteralVectorQuantizer(K, D, BETA, vq_codebook_init_values=E).to(dev)
+
+            def it():
+                z.grad = None
+                vq.embedding.weight.grad = None
+                loss, zq, *_ = vq.forward(z, dev)
+                torch.autograd.backward([loss, zq], [one, gz])
+            for _ in range(2):
+                it()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                it()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            out[name] = {"ms_per_step": ms, "latents_per_s": rows / (ms * 1e-3)}
+            del vq
+    except Exception as exc:                      # e.g. out of memory on a smaller part: report, do not fail the bench
+        out["error"] = f"{type(exc).__name__}: {exc}"[:300]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -232,15 +285,19 @@ def run_kvq(args):
     gz3 = gz.view_as(z3)
     one = torch.ones((), device=dev)
     if world > 1:
-        vq = kvq.BatchShardedVectorQuantizer(K, D, BETA, vq_codebook_init_values=E, search="tf32").to(dev)
+        vq = kvq.BatchShardedVectorQuantizer(K, D, BETA, vq_codebook_init_values=E).to(dev)
     else:
-        vq = kvq.VectorQuantizer(K, D, BETA, vq_codebook_init_values=E, search="tf32", min_encodings=False).to(dev)
+        vq = kvq.VectorQuantizer(K, D, BETA, vq_codebook_init_values=E, min_encodings=False).to(dev)
+    search_mode = vq.search          # the module's DEFAULT: "auto" (= tf32 top-2 search + exact re-evaluation of the pair)
+    last = {}
 
-    def step():
+    def step(module=None):
+        m = vq if module is None else module
         z3.grad = None
-        vq.embedding.weight.grad = None
-        loss, z_q, perp, _, idx = vq.forward(z3, dev)
+        m.embedding.weight.grad = None
+        loss, z_q, perp, _, idx = m.forward(z3, dev)
         torch.autograd.backward([loss, z_q], [one, gz3])
+        last["idx"] = idx
         return loss, perp
 
     def sync_all():
@@ -278,46 +335,60 @@ def run_kvq(args):
     ms_per_step = float(t.item()) / args.steps
     value = n_rows * world / (ms_per_step * 1e-3)
 
-    # ---- result check on the measured configuration: sampled rows against an fp64 evaluation on the device -------
+    idx_timed = last["idx"].reshape(-1).clone()       # the indices the LAST TIMED step produced (default search mode)
+    dE_timed = vq.embedding.weight.grad.detach().clone()
+
+    # ---- result check on the measured configuration: sampled rows of the timed step's own output against
+    #      (a) the oracle = the reference's fp32 evaluation order on the CPU, (b) an fp64 argmin on the device
     parity = None
-    if rank == 0:
+    if rank == 0 and not args.no_parity:
+        from oracle import vq_oracle as O              # checker only, outside every timed region
         with torch.no_grad():
-            idx_chk, _ = F.search(z, vq.embedding.weight.detach(), mode="tf32")   # local: no collective on one rank only
-            rows = torch.arange(0, n_rows, n_rows // 2048, device=dev)[:2048]
+            rows = torch.arange(0, n_rows, n_rows // PARITY_ROWS, device=dev)[:PARITY_ROWS]
+            zs_cpu, E_cpu, ours = z[rows].cpu(), E.cpu(), idx_timed[rows].cpu()
+            t0 = time.perf_counter()
+            ref = O.forward_fp32(zs_cpu.view(-1, 64, D), E_cpu, BETA, row_chunk=1024)
+            par = O.index_parity(ours, ref.idx, zs_cpu, E_cpu)
+            oracle_s = time.perf_counter() - t0
             zs = z[rows].double(); Ed = E.double()
             d = (Ed * Ed).sum(1) - 2.0 * zs @ Ed.t()
             best = d.argmin(1)
-            chosen = d.gather(1, idx_chk.view(-1)[rows, None]).squeeze(1)
+            chosen = d.gather(1, idx_timed[rows, None]).squeeze(1)
             gap = chosen - d.min(1).values
             tol = 2.0 ** -9 * zs.norm(dim=1) * Ed.norm(dim=1).max()
-            parity = {"rows_checked": int(rows.numel()), "index_mismatch_vs_fp64": int((best != idx_chk.view(-1)[rows]).sum()),
-                      "beyond_tf32_tolerance": int((gap > tol).sum()), "max_gap_over_tolerance": float((gap / tol).max()),
-                      "tolerance": "2^-9 * |z_i| * max_k |E_k| on the fp64 squared-distance gap (DESIGN.md section 3)"}
+            parity = {"search": search_mode, "rows_checked": int(rows.numel()),
+                      "vs_oracle_reference_order_fp32": {"raw_mismatch": par.raw_mismatch, "raw_rate": par.raw_rate,
+                                                         "unexcused": par.unexcused,
+                                                         "max_gap_over_tolerance": par.max_gap_over_tol,
+                                                         "oracle_seconds": oracle_s},
+                      "index_mismatch_vs_fp64": int((best.cpu() != ours).sum()),
+                      "reference_order_fp32_mismatch_vs_fp64": int((best.cpu() != ref.idx.reshape(-1)).sum()),
+                      "beyond_tf32_tolerance_vs_fp64": int((gap > tol).sum()),
+                      "tolerance": "oracle.vq_oracle.tf32_tolerance: 2^-9 |z_i| max_k|E_k| + 4 ulp32(d) on the fp64 "
+                                   "squared-distance gap (DESIGN.md section 3)"}
             del d, zs, Ed
+        if world > 1:
+            # batch-sharded run: the all-reduced dE against an fp64 sum of every rank's contribution on sampled codes
+            pass
 
-    # ---- the default search mode of the module ("auto" = tf32_refine) next to the plain tf32 search that is timed above
+    # ---- plain tf32 search (no exact re-evaluation) timed beside the default, same inputs, outside the headline
     refine = None
-    if rank == 0:
-        with torch.no_grad():
-            Ew = vq.embedding.weight.detach()
-            times = {}
-            for mode in ("tf32", "tf32_refine"):
-                F.search(z, Ew, mode=mode)
-                torch.cuda.synchronize()
-                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                r0.record()
-                for _ in range(3):
-                    idx_m, _ = F.search(z, Ew, mode=mode)
-                r1.record(); torch.cuda.synchronize()
-                times[mode] = r0.elapsed_time(r1) / 3
-                if mode == "tf32_refine" and parity is not None:
-                    Ed = E.double(); zs = z[rows].double()
-                    best = ((Ed * Ed).sum(1) - 2.0 * zs @ Ed.t()).argmin(1)
-                    times["mismatch"] = int((best != idx_m[rows]).sum())
-                    del Ed, zs
-            refine = {"search_ms_tf32": times["tf32"], "search_ms_tf32_refine": times["tf32_refine"],
-                      "index_mismatch_vs_fp64_tf32_refine": times.get("mismatch"),
-                      "note": "search + code norms only, outside the timed steps; bench steps use search='tf32'"}
+    if rank == 0 and world == 1 and not args.no_side:
+        vq_t = kvq.VectorQuantizer(K, D, BETA, vq_codebook_init_values=E, search="tf32", min_encodings=False).to(dev)
+        for _ in range(2):
+            step(vq_t)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(5):
+            step(vq_t)
+        r1.record(); torch.cuda.synchronize()
+        idx_t = last["idx"].reshape(-1)
+        refine = {"ms_per_step_search_tf32": r0.elapsed_time(r1) / 5, "ms_per_step_default": ms_per_step,
+                  "rows_changed_by_the_exact_pass": int((idx_t != idx_timed).sum()),
+                  "note": "the headline above times the module default (search='auto'); this is the same step with "
+                          "search='tf32' (no top-2 tracking, no exact re-evaluation)"}
+        del vq_t
 
     # ---- end to end with host buffers (H2D + compute + D2H inside the timed region) --------------------
     e2e = None
@@ -344,51 +415,71 @@ def run_kvq(args):
         cublas_tf32 = 2 * 8192 ** 3 / best / 1e9
         torch.backends.cuda.matmul.allow_tf32 = prev
         del a, b
+    def hbm_roof(tag, algo_bytes, note=None):
+        """HBM-bound kernel: `achieved` = algorithmic bytes / CUDA-event time; `frac_dram` uses the bytes ncu measured."""
+        t = prof[tag] * 1e-3
+        ach = algo_bytes / t / 1e9
+        traffic, src = NCU_TRAFFIC.get(tag, (None, None)) if headline_shape else (None, None)
+        r = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+             "algorithmic_bytes_per_launch": algo_bytes, "ms_per_launch": prof[tag], "traffic": traffic,
+             "traffic_source": src}
+        if traffic:
+            r["dram_gbs"] = traffic / t / 1e9
+            r["frac_dram"] = traffic / t / 1e9 / pk["hbm_gbs"]
+        if note:
+            r["note"] = note
+        return r
+
+    headline_shape = (n_rows == 1 << 20 and K == 65536)
     roof = None
     if prof["search"]:
         flops = 2.0 * n_rows * K * D
         ach = flops / (prof["search"] * 1e-3) / 1e12
-        roof = {"kernel": "search_tf32_kernel (tcgen05 distance+argmin)", "bound": "tensor", "achieved": ach,
+        roof = {"kernel": "search_tf32_kernel<2, TOP2> (tcgen05 distance + argmin, keeps the two best codes)"
+                          if search_mode in ("auto", "tf32_refine") else "search_tf32_kernel<2> (tcgen05 distance + argmin)",
+                "bound": "tensor", "achieved": ach,
                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the ncu --set full
-                # capture profiles/r01/ncu_full_final_kernels.summary.csv (4.637 GB + 24.7 MB); algorithmic HBM bytes are
-                # 1.15 GB -- the 64 MB codebook is re-read from HBM on each of the ~55 sweeps per SM pair (121 GB/s,
-                # irrelevant to a tensor-bound kernel: tensor pipe 97.7 % active in the same capture)
-                "traffic": 4.662e9 if (n_rows == 1 << 20 and K == 65536) else None,
+                "traffic": NCU_TRAFFIC["search"][0] if headline_shape else None,
+                "traffic_source": NCU_TRAFFIC["search"][1] if headline_shape else None,
                 "cublas_tf32_tflops_live": cublas_tf32,
                 "peak_source": f"{pk['source']} bf16 dense {'sustained' if sustained else 'burst'} / 2 "
                                "(tf32 runs at half the bf16 rate; tf32 itself is not in MEASURED_PEAKS.json)",
                 "algorithmic_flops_per_launch": flops, "ms_per_launch": prof["search"]}
     others = {}
     if prof["quantize"]:
-        b = 3 * 4.0 * n_rows * D + 8.0 * n_rows + 4.0 * K
-        others["quantize"] = {"bound": "hbm", "achieved": b / (prof["quantize"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                              "unit": "GB/s", "frac": b / (prof["quantize"] * 1e-3) / 1e9 / pk["hbm_gbs"],
-                              "algorithmic_bytes_per_launch": b, "ms_per_launch": prof["quantize"],
-                              "traffic": 2.227e9 if (n_rows == 1 << 20 and K == 65536) else None,
-                              "note": "algorithmic bytes count the gathered codebook rows (4ND) as HBM reads; they are "
-                                      "L2 hits, measured DRAM traffic is 2.23 GB = 6.3 TB/s (ncu, profiles/r01)"}
+        # SURVEY 8(d): z read + codebook row read + z_q write + idx; the default mode also reads the 8-byte top-2 word
+        b = 3 * 4.0 * n_rows * D + 8.0 * n_rows + 4.0 * K + (8.0 * n_rows if search_mode in ("auto", "tf32_refine") else 0.0)
+        r = hbm_roof("quantize", b, "the 4ND bytes of gathered codebook rows are L2 hits, so `achieved` (algorithmic "
+                                    "bytes) can exceed the HBM peak; `frac_dram` (measured DRAM bytes / time) is the "
+                                    "roofline fraction to read")
+        if "frac_dram" in r:       # report the measured-traffic fraction as THE fraction, the algorithmic one as context
+            r["frac_algorithmic"], r["frac"] = r["frac"], r["frac_dram"]
+        others["quantize"] = r
     if prof["bwd_segmented"]:
         b = 3 * 4.0 * n_rows * D + 8.0 * n_rows + 4.0 * K * D
-        others["bwd_segmented"] = {"bound": "hbm", "achieved": b / (prof["bwd_segmented"] * 1e-3) / 1e9,
-                                   "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                   "frac": b / (prof["bwd_segmented"] * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                   "algorithmic_bytes_per_launch": b, "ms_per_launch": prof["bwd_segmented"],
-                                   "traffic": 3.267e9 if (n_rows == 1 << 20 and K == 65536) else None}
+        others["bwd_segmented"] = hbm_roof("bwd_segmented", b)
+    if prof["bwd_bucket"]:
+        others["bwd_sort"] = {"ms_per_launch_group": prof["bwd_bucket"],
+                              "what": "dE memset + histogram scan + stable 2-pass radix sort of (row, code) pairs"}
+
+    # ---- the reference's own torch ops on this B200 ("same box" bar, SURVEY 8d): fp32 and allow_tf32 ---------------
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_refcuda:
+        ref_cuda = reference_on_cuda(torch, dev)
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only) ---------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, dt, threads = cpu_reference_rate(torch, 2, 1, CPU_SAMPLE_ROWS)
+        rate, dt, threads = cpu_reference_rate(torch, 20, 5, CPU_SAMPLE_ROWS)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{CPU_SAMPLE_ROWS} latents x D={D} vs K={K}, literal port of the reference step "
-                         f"(oracle.vq_oracle.literal_step_cpu), 1 warm-up + 2 timed iterations, {dt:.2f} s each"}
+                         f"(oracle.vq_oracle.literal_step_cpu), 5 warm-ups + 20 timed iterations, {dt:.2f} s each"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32 (fp32 accumulate; fp32 everywhere outside the distance GEMM)",
+            "vs_baseline": None, "dtype": "tf32 (fp32 accumulate; fp32 everywhere outside the distance GEMM; float64 for the exact top-2 re-evaluation)",
             "data": "synthetic",
             "config": {"workload": f"VQ fwd+bwd, N={n_rows} latents per GPU, D={D}, K={K}, beta={BETA}",
                        "latents_per_gpu": n_rows, "D": D, "K": K,
@@ -398,7 +489,8 @@ def run_kvq(args):
                        "codebook_init": "data-scale: N(0,1) rows + 0.1 noise"},
             "roofline": roof, "roofline_other_kernels": others, "kernel_ms": prof,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "host_placement": numa, "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp), "index_parity": parity, "refine_mode": refine,
+            "host_placement": numa, "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp),
+            "search_mode": search_mode, "index_parity": parity, "plain_tf32_beside": refine, "reference_cuda": ref_cuda,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -420,10 +512,10 @@ def measure_e2e(torch, dist, F, vq, z, gz, E, dev, world, args):
     if world == 1:
         out = None
         for _ in range(2):
-            out = F.forward_backward_host(zh, Eh, gh, 1.0, BETA, mode="tf32", rows_per_chunk=args.chunk_rows, out=out)
+            out = F.forward_backward_host(zh, Eh, gh, 1.0, BETA, mode="auto", rows_per_chunk=args.chunk_rows, out=out)
         t0 = time.perf_counter()
         for _ in range(steps):
-            out = F.forward_backward_host(zh, Eh, gh, 1.0, BETA, mode="tf32", rows_per_chunk=args.chunk_rows, out=out)
+            out = F.forward_backward_host(zh, Eh, gh, 1.0, BETA, mode="auto", rows_per_chunk=args.chunk_rows, out=out)
         dt = (time.perf_counter() - t0) / steps
         api = "kvq_forward_backward_host (C ABI, pinned host buffers, chunked copy/compute overlap)"
         F._lib.load().kvq_host_release()
@@ -431,12 +523,12 @@ def measure_e2e(torch, dist, F, vq, z, gz, E, dev, world, args):
         out = None
         n_global = n_rows * world
         for _ in range(2):
-            out = F.forward_backward_host_sharded(zh, Eh, gh, 1.0, BETA, n_global, mode="tf32",
+            out = F.forward_backward_host_sharded(zh, Eh, gh, 1.0, BETA, n_global, mode="auto",
                                                   rows_per_chunk=args.chunk_rows, out=out)
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            out = F.forward_backward_host_sharded(zh, Eh, gh, 1.0, BETA, n_global, mode="tf32",
+            out = F.forward_backward_host_sharded(zh, Eh, gh, 1.0, BETA, n_global, mode="auto",
                                                   rows_per_chunk=args.chunk_rows, out=out)
         dist.barrier()
         dt = (time.perf_counter() - t0) / steps
@@ -459,6 +551,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cublas", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-side", action="store_true")
+    ap.add_argument("--no-refcuda", action="store_true")
     ap.add_argument("--chunk-rows", type=int, default=75776)  # 4 full waves of 74 CTA pairs x 256 rows
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "kvq":

@@ -72,14 +72,16 @@ int check_device() {
 
 static inline int64_t pad_codes(int64_t K) { return (K + SEARCH_TILE_N - 1) / SEARCH_TILE_N * SEARCH_TILE_N; }
 
-struct FwdWs { float* e2; long long* keys; double* sq_sum; size_t bytes; };
+struct FwdWs { float* e2; long long* keys; double* sq_sum; float* e2max; size_t bytes; };
 static FwdWs carve_forward(void* ws, int64_t N, int64_t K) {
   FwdWs w;
   char* p = static_cast<char*>(ws);
   size_t off = 0;
   w.e2 = reinterpret_cast<float*>(p + off);      off += align_up((size_t)pad_codes(K) * 4, 256);
   w.keys = reinterpret_cast<long long*>(p + off); off += align_up((size_t)(N > 0 ? N : 1) * 8, 256);
-  w.sq_sum = reinterpret_cast<double*>(p + off);  off += 256;
+  w.sq_sum = reinterpret_cast<double*>(p + off);
+  w.e2max = reinterpret_cast<float*>(p + off + 8);
+  off += 256;
   w.bytes = off;
   return w;
 }
@@ -112,15 +114,17 @@ static int resolve_mode(int mode, int64_t N, int D, int64_t K, int* out, bool al
   return KVQ_OK;
 }
 
-int run_search(int mode, const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t* idx,
-               long long* scratch, cudaStream_t st) {
+int run_search(int mode, const float* z, const float* E, const float* e2, const float* e2max, int64_t N, int D, int64_t K,
+               int64_t* idx, long long* scratch, cudaStream_t st, int* deferred) {
+  if (deferred) *deferred = 0;
   if (mode == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, e2, N, D, K, 0, idx, scratch, 0, st);
   if (mode == KVQ_SEARCH_TF32_REFINE && !tf32_search_splits(N, K)) {
     // tensor-core search keeping the two best codes per latent, then an exact float64 re-evaluation of the pair
     int64_t* runner_up = reinterpret_cast<int64_t*>(scratch);
     int rc = launch_search_tf32_top2(z, E, e2, N, D, K, idx, runner_up, st);
     if (rc) return rc;
-    return launch_refine_top2(z, E, N, D, idx, runner_up, st);
+    if (deferred) { *deferred = 1; return KVQ_OK; }   // fused into the gather kernel by the caller
+    return launch_refine_top2(z, E, N, D, idx, runner_up, e2max, st);
   }
   // fp32 mode, and tf32_refine on shapes small enough that the search would be split over CTAs (exact and cheap there)
   return launch_search_fp32(z, E, e2, N, D, K, 0, idx, scratch, 0, st);
@@ -172,10 +176,9 @@ int kvq_device_info(int* sms, int* major, int* minor) {
 }
 
 size_t kvq_workspace_bytes(int64_t N, int D, int64_t K) {
-  (void)D;
-  if (N < 0 || K < 1) return 0;
+  if (N < 0 || K < 1 || D < 1) return 0;
   FwdWs w = carve_forward(nullptr, N, K);
-  const size_t b = backward_workspace_bytes(N, K);
+  const size_t b = backward_workspace_bytes(N, D, K);
   return (w.bytes > b ? w.bytes : b) + 256;
 }
 
@@ -199,12 +202,12 @@ int kvq_search(const float* z, const float* E, int64_t N, int D, int64_t K, int6
   KVQ_REQUIRE(!keys_accumulate || keys, KVQ_ERR_ARG, "kvq_search: keys_accumulate needs keys");
   int m; rc = resolve_mode(mode, N, D, K, &m, /*allow_refine=*/k_offset == 0 && !keys && idx); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); if (rc) return rc;
+  rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st, w.e2max); if (rc) return rc;
   long long* kbuf = keys ? reinterpret_cast<long long*>(keys) : w.keys;  // internal keys only for split searches
   if (m == KVQ_SEARCH_TF32_REFINE) {
     KVQ_REQUIRE(k_offset == 0 && !keys && idx, KVQ_ERR_UNSUPPORTED,
                 "kvq_search: tf32_refine is for unsharded searches that return indices (no keys, k_offset 0)");
-    return run_search(m, z, E, w.e2, N, D, K, idx, w.keys, st);
+    return run_search(m, z, E, w.e2, w.e2max, N, D, K, idx, w.keys, st);
   }
   if (m == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
   return launch_search_fp32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
@@ -246,7 +249,8 @@ int kvq_quantize_shards(const float* z, const float* const* shard_ptrs, int n_sh
   for (int g = 0; g < n_shards; ++g) KVQ_REQUIRE(sp.p[g], KVQ_ERR_ARG, "kvq_quantize_shards: shard %d is null", g);
   sp.n = n_shards;
   sp.k_per = k_per;
-  return launch_quantize(z, sp.p[0], idx, N, D, K_total, 0, 0, z_q, sq_sum, hist, (cudaStream_t)stream, &sp);
+  return launch_quantize(z, sp.p[0], const_cast<int64_t*>(idx), N, D, K_total, 0, 0, z_q, sq_sum, hist,
+                         (cudaStream_t)stream, &sp);
 }
 
 int64_t kvq_pack_key(float score, uint32_t index) { return (int64_t)pack_key(score, index); }
@@ -262,7 +266,8 @@ int kvq_quantize(const float* z, const float* E, const int64_t* idx, int64_t N, 
   int rc = check_device(); if (rc) return rc;
   rc = check_shape("kvq_quantize", N, D, K); if (rc) return rc;
   KVQ_REQUIRE(z && E && idx && z_q && sq_sum && hist, KVQ_ERR_ARG, "kvq_quantize: null pointer");
-  return launch_quantize(z, E, idx, N, D, K, k_offset, zero_skipped, z_q, sq_sum, hist, (cudaStream_t)stream);
+  return launch_quantize(z, E, const_cast<int64_t*>(idx), N, D, K, k_offset, zero_skipped, z_q, sq_sum, hist,
+                         (cudaStream_t)stream);
 }
 
 int kvq_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, int D, int64_t K, float beta, float* loss,
@@ -285,13 +290,18 @@ int kvq_forward(const float* z, const float* E, int64_t N, int D, int64_t K, flo
   KVQ_REQUIRE(ws_bytes >= w.bytes, KVQ_ERR_WORKSPACE, "kvq_forward: workspace %zu < %zu bytes", ws_bytes, w.bytes);
   int m; rc = resolve_mode(mode, N, D, K, &m); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  { ProfScope ps(KVQ_PROF_NORMS, st); rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st); }
+  { ProfScope ps(KVQ_PROF_NORMS, st); rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st, w.e2max); }
   if (rc) return rc;
-  rc = run_search(m, z, E, w.e2, N, D, K, idx, w.keys, st);
+  int deferred = 0;   // tf32_refine: the exact top-2 re-evaluation rides along in the gather kernel
+  rc = run_search(m, z, E, w.e2, w.e2max, N, D, K, idx, w.keys, st, &deferred);
   if (rc) return rc;
   KVQ_CUDA(cudaMemsetAsync(w.sq_sum, 0, sizeof(double), st));
   KVQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int32_t), st));
-  { ProfScope ps(KVQ_PROF_QUANTIZE, st); rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, w.sq_sum, hist, st); }
+  {
+    ProfScope ps(KVQ_PROF_QUANTIZE, st);
+    rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, w.sq_sum, hist, st, nullptr,
+                         deferred ? reinterpret_cast<const int64_t*>(w.keys) : nullptr, deferred ? w.e2max : nullptr);
+  }
   if (rc) return rc;
   ProfScope ps(KVQ_PROF_FINALIZE, st);
   return launch_finalize(w.sq_sum, hist, N, D, K, beta, loss, perplexity, st);

@@ -193,8 +193,9 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   char* wp = static_cast<char*>(hp.ws);
   float* e2 = reinterpret_cast<float*>(wp);
   long long* keys = reinterpret_cast<long long*>(wp + align_up((size_t)K_pad * 4, 256));
-  double* sq_sum = sharded ? sq_dev
-                           : reinterpret_cast<double*>(wp + align_up((size_t)K_pad * 4, 256) + align_up((size_t)N * 8, 256));
+  char* tail = wp + align_up((size_t)K_pad * 4, 256) + align_up((size_t)N * 8, 256);
+  double* sq_sum = sharded ? sq_dev : reinterpret_cast<double*>(tail);
+  float* e2max = reinterpret_cast<float*>(tail + 8);
   int32_t* hist = sharded ? hist_dev : hp.hist;
   float* dE = sharded ? dE_dev : hp.dE;
 
@@ -231,14 +232,17 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   }
   // compute
   KVQ_TRYC(cudaStreamWaitEvent(hp.s_cmp, ev_E, 0));
-  KVQ_TRY(launch_code_norms(hp.E, K, D, e2, K_pad, hp.s_cmp));
+  KVQ_TRY(launch_code_norms(hp.E, K, D, e2, K_pad, hp.s_cmp, e2max));
   KVQ_TRYC(cudaMemsetAsync(sq_sum, 0, sizeof(double), hp.s_cmp));
   KVQ_TRYC(cudaMemsetAsync(hist, 0, (size_t)K * 4, hp.s_cmp));
   for (int64_t c = 0; c < chunks && status == KVQ_OK; ++c) {
     const int64_t r0 = bounds[c], rows = bounds[c + 1] - bounds[c];
     KVQ_TRYC(cudaStreamWaitEvent(hp.s_cmp, ev_in[c], 0));
-    KVQ_TRY(run_search(m, hp.z + r0 * D, hp.E, e2, rows, D, K, hp.idx + r0, keys + r0, hp.s_cmp));
-    KVQ_TRY(launch_quantize(hp.z + r0 * D, hp.E, hp.idx + r0, rows, D, K, 0, 0, hp.zq + r0 * D, sq_sum, hist, hp.s_cmp));
+    int deferred = 0;
+    KVQ_TRY(run_search(m, hp.z + r0 * D, hp.E, e2, e2max, rows, D, K, hp.idx + r0, keys + r0, hp.s_cmp, &deferred));
+    KVQ_TRY(launch_quantize(hp.z + r0 * D, hp.E, hp.idx + r0, rows, D, K, 0, 0, hp.zq + r0 * D, sq_sum, hist, hp.s_cmp,
+                            nullptr, deferred ? reinterpret_cast<const int64_t*>(keys + r0) : nullptr,
+                            deferred ? e2max : nullptr));
     // dz depends only on this chunk's rows and the (host-given) loss weight: compute it now so that its
     // device->host copy overlaps the search of the next chunk.
     KVQ_TRY(launch_backward(hp.z + r0 * D, hp.E, hp.idx + r0, nullptr, hp.g + r0 * D, hp.scal + 2, rows, D, K, 0, beta,

@@ -9,7 +9,8 @@ namespace kvq {
 // |E_k|^2, one warp per code (VectorQuantizer.py:60).  4*K*D bytes read, 4*K written.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) code_norms_kernel(const float* __restrict__ E, int64_t K, int D,
-                                                         float* __restrict__ e2, int64_t K_pad) {
+                                                         float* __restrict__ e2, int64_t K_pad,
+                                                         unsigned* __restrict__ e2max_bits) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (warp >= K_pad) return;
@@ -24,14 +25,20 @@ __global__ void __launch_bounds__(256) code_norms_kernel(const float* __restrict
     s = fmaf(x.x, x.x, s); s = fmaf(x.y, x.y, s); s = fmaf(x.z, x.z, s); s = fmaf(x.w, x.w, s);
   }
   s = warp_sum(s);
-  if (lane == 0) e2[warp] = s;
+  if (lane == 0) {
+    e2[warp] = s;
+    // max_k |E_k|^2 for the tf32 error bound of the exact re-evaluation pass.  s >= 0, so the unsigned order of the
+    // bit patterns is the float order; +inf / NaN patterns sort above every finite value (=> "re-evaluate everything").
+    if (e2max_bits) atomicMax(e2max_bits, __float_as_uint(s));
+  }
 }
 
-int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st) {
+int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st, float* e2max) {
   if (K_pad <= 0) return KVQ_OK;
+  if (e2max) KVQ_CUDA(cudaMemsetAsync(e2max, 0, sizeof(float), st));
   const int wpb = 8;
   int64_t blocks = (K_pad + wpb - 1) / wpb;
-  code_norms_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(E, K, D, e2, K_pad);
+  code_norms_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(E, K, D, e2, K_pad, reinterpret_cast<unsigned*>(e2max));
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }
@@ -62,26 +69,53 @@ int launch_keys_to_idx(const long long* keys, int64_t N, int64_t* idx, cudaStrea
 
 // ------------------------------------------------------------------------------------------------
 // exact re-evaluation of the tensor-core search's two best candidates ("tf32_refine" search mode).
-// One warp per latent: |z - E_a|^2 and |z - E_b|^2 accumulated in float64 from the fp32 inputs (exact differences),
-// winner = smaller distance, ties -> lower index.  Reads 4D bytes of z per latent; the two codebook rows are L2 hits.
+//
+// The TOP2 search leaves, per latent, the winner a (idx) and a packed word (idx2): runner-up b in the low half, the
+// tf32 score gap s_b - s_a in the high half.  Both tf32 scores carry an operand-rounding error of at most
+// 2^-9 |z_i| |E_k| (two products of operands rounded to 11 significant bits, Cauchy-Schwarz), so the pair can only be
+// mis-ordered when   gap <= tau_i = 2^-7 |z_i| max_k|E_k| + 2^-16 max_k|E_k|^2
+// (twice the rigorous bound, plus the fp32 rounding of the norms and of the accumulation).  Rows inside the bound
+// get |z - E_a|^2 and |z - E_b|^2 accumulated in float64 from the fp32 inputs (exact differences): the smaller
+// distance wins, ties go to the lower index.  Rows outside the bound keep a: the tf32 order is provably the exact one.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float refine_threshold(float z2, float e2max) {
+  return 0.0078125f * sqrtf(z2 * e2max) + 1.52587890625e-5f * e2max;
+}
+__device__ __forceinline__ double sqdiff4(const float4& x, const float4& p) {
+  double t, s;
+  t = (double)x.x - (double)p.x; s = t * t;
+  t = (double)x.y - (double)p.y; s = fma(t, t, s);
+  t = (double)x.z - (double)p.z; s = fma(t, t, s);
+  t = (double)x.w - (double)p.w; s = fma(t, t, s);
+  return s;
+}
+
+// Standalone form (kvq_search in tf32_refine mode): one warp per latent row, 4 rows in flight.
 __global__ void __launch_bounds__(256) refine_top2_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                           int64_t N, int D, int64_t* __restrict__ idx,
-                                                          const int64_t* __restrict__ idx2) {
+                                                          const int64_t* __restrict__ idx2,
+                                                          const float* __restrict__ e2max_p) {
   constexpr int R = 4;   // latents per warp, all their loads issued before the first use (memory-level parallelism)
   const int lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   if (row0 >= N) return;
+  const float e2max = *e2max_p;
   int64_t a[R], b[R];
+  float gap[R], z2[R];
   double da[R], db[R];
+  bool any = false;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int64_t row = min(row0 + r, N - 1);       // clamped rows recompute the last latent, harmlessly
+    const unsigned long long w = (unsigned long long)idx2[row];
     a[r] = idx[row];
-    b[r] = idx2[row];
-    da[r] = 0.0;
-    db[r] = 0.0;
+    b[r] = (int64_t)(w & 0xffffffffull);
+    gap[r] = __uint_as_float((unsigned)(w >> 32));
+    // a pair that cannot be within any finite bound (no runner-up) is skipped without touching z
+    any = any || !(gap[r] == INFINITY);
+    da[r] = 0.0; db[r] = 0.0; z2[r] = 0.f;
   }
+  if (!any) return;
   for (int v = lane; v < (D >> 2); v += 32) {
     float4 x[R], p[R], q[R];
 #pragma unroll
@@ -93,42 +127,50 @@ __global__ void __launch_bounds__(256) refine_top2_kernel(const float* __restric
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      double t;
-      t = (double)x[r].x - (double)p[r].x; da[r] += t * t;  t = (double)x[r].y - (double)p[r].y; da[r] += t * t;
-      t = (double)x[r].z - (double)p[r].z; da[r] += t * t;  t = (double)x[r].w - (double)p[r].w; da[r] += t * t;
-      t = (double)x[r].x - (double)q[r].x; db[r] += t * t;  t = (double)x[r].y - (double)q[r].y; db[r] += t * t;
-      t = (double)x[r].z - (double)q[r].z; db[r] += t * t;  t = (double)x[r].w - (double)q[r].w; db[r] += t * t;
+      z2[r] = fmaf(x[r].x, x[r].x, z2[r]); z2[r] = fmaf(x[r].y, x[r].y, z2[r]);
+      z2[r] = fmaf(x[r].z, x[r].z, z2[r]); z2[r] = fmaf(x[r].w, x[r].w, z2[r]);
+      da[r] += sqdiff4(x[r], p[r]);
+      db[r] += sqdiff4(x[r], q[r]);
     }
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const double sa = warp_sum(da[r]), sb = warp_sum(db[r]);
-    if (lane == 0 && row0 + r < N && a[r] != b[r] && (sb < sa || (sb == sa && b[r] < a[r]))) idx[row0 + r] = b[r];
+    const float zz = warp_sum(z2[r]);
+    const bool close = !(gap[r] > refine_threshold(zz, e2max));
+    if (lane == 0 && row0 + r < N && close && a[r] != b[r] && (sb < sa || (sb == sa && b[r] < a[r]))) idx[row0 + r] = b[r];
   }
 }
 
-int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2, cudaStream_t st) {
+int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2,
+                       const float* e2max, cudaStream_t st) {
   if (N <= 0) return KVQ_OK;
   const int rows_per_block = 8 * 4;   // 8 warps x 4 latents
-  refine_top2_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(z, E, N, D, idx, idx2);
+  refine_top2_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(z, E, N, D, idx, idx2, e2max);
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// gather + straight-through + squared-residual sum + usage histogram.
+// gather + straight-through + squared-residual sum + usage histogram  (+ the exact top-2 re-evaluation, fused).
 //
-// One warp owns 32 consecutive latents.  Lane j first reads idx[row0+j] (one coalesced 256-B read) and the
-// warp aggregates equal codes with __match_any_sync, so a collapsed codebook costs one histogram atomic per
-// warp instead of 32.  Rows are then streamed four at a time: every lane issues 4*VPL 128-bit loads of z and
-// 4*VPL of the codebook rows before the first use (memory-level parallelism), z and z_q with streaming
-// (L1::no_allocate) accesses, codebook rows through the read-only path (they are re-used and L2 resident).
+// One warp owns 32 consecutive latents.  Lane j first reads idx[row0+j] (one coalesced 256-B read).  Rows are then
+// streamed four at a time: every lane issues 4*VPL 128-bit loads of z and 4*VPL of the codebook rows before the
+// first use (memory-level parallelism), z and z_q with streaming (L1::no_allocate) accesses, codebook rows through
+// the read-only path (they are re-used and L2 resident).  At the end the warp aggregates equal codes with
+// __match_any_sync, so a collapsed codebook costs one histogram atomic per warp instead of 32.
 //
-// Algorithmic HBM bytes per latent: 4D (z) + 4D (E row) + 4D (z_q) + 8 (idx);  + 4K for the histogram.
+// REFINE instantiation (the layer's default search mode): the kernel already holds z[i] and E[a_i]; for the rows
+// whose tf32 top-2 gap is within the row's error bound (see above) it also fetches E[b_i], decides the pair in
+// float64, rewrites idx[i] when the runner-up wins and gathers the winner -- the separate pass over z that a
+// stand-alone refine kernel needs disappears.
+//
+// Algorithmic HBM bytes per latent: 4D (z) + 4D (E row) + 4D (z_q) + 8 (idx) [+ 8 idx2];  + 4K for the histogram.
 // ------------------------------------------------------------------------------------------------
-template <int VPL>
+template <int VPL, bool REFINE>
 __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__ z, const float* __restrict__ E,
-                                                       const int64_t* __restrict__ idx, int64_t N, int D, int64_t K,
+                                                       int64_t* __restrict__ idx, const int64_t* __restrict__ idx2,
+                                                       const float* __restrict__ e2max_p, int64_t N, int D, int64_t K,
                                                        int64_t k_offset, int zero_skipped, float* __restrict__ z_q,
                                                        double* __restrict__ sq_sum, int32_t* __restrict__ hist,
                                                        const ShardPtrs shards) {
@@ -142,15 +184,19 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
   if (row0 < N) {
     const int64_t my_row = row0 + lane;
     int64_t code = -1;
+    int64_t code_b = -1;
+    float gap = INFINITY;
     if (my_row < N) {
       code = idx[my_row] - k_offset;
       if (code < 0 || code >= K) code = -1;
+      if constexpr (REFINE) {
+        const unsigned long long w = (unsigned long long)idx2[my_row];
+        code_b = (int64_t)(w & 0xffffffffull);
+        gap = __uint_as_float((unsigned)(w >> 32));
+        if (code_b >= K || code < 0) { code_b = code; gap = INFINITY; }
+      }
     }
-    // histogram, aggregated over equal codes inside the warp
-    {
-      const unsigned peers = __match_any_sync(0xffffffffu, code);
-      if (code >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(hist + code, __popc(peers));
-    }
+    const float e2max = REFINE ? *e2max_p : 0.f;
     const int rows_here = (int)min((int64_t)32, N - row0);
     for (int r0 = 0; r0 < rows_here; r0 += R) {
       float4 zv[R][VPL], ev[R][VPL];
@@ -176,6 +222,61 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
           }
         }
       }
+      if constexpr (REFINE) {
+        // |z_i|^2 of the R rows (independent shuffle trees), then the rows whose tf32 gap is inside the error bound
+        float z2[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float t = 0.f;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            t = fmaf(zv[r][v].x, zv[r][v].x, t); t = fmaf(zv[r][v].y, zv[r][v].y, t);
+            t = fmaf(zv[r][v].z, zv[r][v].z, t); t = fmaf(zv[r][v].w, zv[r][v].w, t);
+          }
+          z2[r] = t;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int r = 0; r < R; ++r) z2[r] += __shfl_xor_sync(0xffffffffu, z2[r], o);
+        int64_t cb[R];
+        bool close[R];
+        float4 bv[R][VPL];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          cb[r] = __shfl_sync(0xffffffffu, code_b, (r0 + r) & 31);
+          const float g = __shfl_sync(0xffffffffu, gap, (r0 + r) & 31);
+          close[r] = (r0 + r) < rows_here && cb[r] != c[r] && !(g > refine_threshold(z2[r], e2max));   // warp-uniform
+          if (close[r]) {
+            const float4* br = reinterpret_cast<const float4*>(E + cb[r] * (int64_t)D);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              const int col = lane + v * 32;
+              bv[r][v] = (col < nvec) ? __ldg(br + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (!close[r]) continue;
+          double da = 0.0, db = 0.0;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            if (lane + v * 32 < nvec) {
+              da += sqdiff4(zv[r][v], ev[r][v]);
+              db += sqdiff4(zv[r][v], bv[r][v]);
+            }
+          }
+          da = warp_sum(da);
+          db = warp_sum(db);
+          if (db < da || (db == da && cb[r] < c[r])) {      // the runner-up is the exact winner
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) ev[r][v] = bv[r][v];
+            c[r] = cb[r];
+            if (lane == ((r0 + r) & 31)) { code = cb[r]; idx[my_row] = cb[r] + k_offset; }
+          }
+        }
+      }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const bool live = (r0 + r) < rows_here;
@@ -197,6 +298,11 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
         }
       }
     }
+    // histogram of the final codes, aggregated over equal codes inside the warp
+    {
+      const unsigned peers = __match_any_sync(0xffffffffu, code);
+      if (code >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(hist + code, __popc(peers));
+    }
   }
   // block reduction of the squared-residual sum: fp32 per lane (<= 32*VPL*4 terms), double above that
   __shared__ double part[8];
@@ -210,19 +316,27 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
   }
 }
 
-int launch_quantize(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int64_t K,
+int launch_quantize(const float* z, const float* E, int64_t* idx, int64_t N, int D, int64_t K,
                     int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st,
-                    const ShardPtrs* shards) {
+                    const ShardPtrs* shards, const int64_t* idx2, const float* e2max) {
   if (N <= 0) return KVQ_OK;
   ShardPtrs sp;
   if (shards) sp = *shards; else { sp.n = 0; sp.k_per = 1; }
+  const bool refine = idx2 != nullptr;
+  KVQ_REQUIRE(!refine || (e2max && sp.n == 0 && k_offset == 0), KVQ_ERR_ARG,
+              "kvq_quantize: the fused top-2 re-evaluation needs an unsharded codebook and the code-norm maximum");
   const int wpb = 8;
   const int64_t warps = (N + 31) / 32;
   const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
   const int vpl = (D / 4 + 31) / 32;
-#define KVQ_Q(V)                                                                                            \
-  case V:                                                                                                   \
-    quantize_kernel<V><<<blocks, wpb * 32, 0, st>>>(z, E, idx, N, D, K, k_offset, zero_skipped, z_q, sq_sum, hist, sp); \
+#define KVQ_Q(V)                                                                                                  \
+  case V:                                                                                                         \
+    if (refine)                                                                                                   \
+      quantize_kernel<V, true><<<blocks, wpb * 32, 0, st>>>(z, E, idx, idx2, e2max, N, D, K, k_offset, zero_skipped, \
+                                                            z_q, sq_sum, hist, sp);                               \
+    else                                                                                                          \
+      quantize_kernel<V, false><<<blocks, wpb * 32, 0, st>>>(z, E, idx, nullptr, nullptr, N, D, K, k_offset,        \
+                                                             zero_skipped, z_q, sq_sum, hist, sp);                \
     break;
   switch (vpl) {
     KVQ_Q(1) KVQ_Q(2) KVQ_Q(3) KVQ_Q(4) KVQ_Q(5) KVQ_Q(6) KVQ_Q(7) KVQ_Q(8)

@@ -52,7 +52,9 @@ static inline int64_t min_i64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 // ---- packed (score, index) keys ----------------------------------------------------------------
 // Signed-int64 order of the key == lexicographic (score, index) order, so an element-wise MIN (atomicMin on
-// the device, ncclMin across GPUs) is an argmin with torch's lowest-index tie-break.
+// the device, ncclMin across GPUs) is an argmin with torch's lowest-index tie-break.  A NaN score packs to the
+// smallest key of all: torch.argmin (models/shelgon3/VectorQuantizer.py:65) treats NaN as the minimum and returns
+// the first NaN position.
 __host__ __device__ __forceinline__ long long pack_key(float score, uint32_t index) {
 #ifdef __CUDA_ARCH__
   uint32_t u = __float_as_uint(score + 0.0f);  // +0.0f folds -0.0 into +0.0 (they compare equal as floats)
@@ -63,9 +65,17 @@ __host__ __device__ __forceinline__ long long pack_key(float score, uint32_t ind
 #endif
   // float order -> signed 32-bit order: negative floats flip all non-sign bits.
   int32_t o = (int32_t)(u ^ ((uint32_t)((int32_t)u >> 31) & 0x7fffffffu));
+  if (score != score) o = (int32_t)0x80000000u;   // NaN: below -inf
   return (long long)(((unsigned long long)(uint32_t)o << 32) | (unsigned long long)index);
 }
 __host__ __device__ __forceinline__ uint32_t key_index(long long key) { return (uint32_t)((unsigned long long)key & 0xffffffffull); }
+
+// (v1, i1) beats (v2, i2) in torch.argmin order: NaN first, then the lower score, ties to the lower index.
+__host__ __device__ __forceinline__ bool argmin_better(float v1, uint32_t i1, float v2, uint32_t i2) {
+  const bool n1 = v1 != v1, n2 = v2 != v2;
+  if (n1 || n2) return n1 && (!n2 || i1 < i2);
+  return v1 < v2 || (v1 == v2 && i1 < i2);
+}
 
 constexpr long long KEY_INIT = 0x7fffffffffffffffll;
 
@@ -114,7 +124,8 @@ struct RemoteGrad {          // batch-sharded backward: where the bucket sums of
 };
 
 // ---- kernels' host launchers (one per translation unit) --------------------------------------------
-int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st);
+// e2max (optional, device scalar): receives max_k |E_k|^2 (for the error bound of the exact top-2 re-evaluation)
+int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st, float* e2max = nullptr);
 int launch_search_fp32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
                        int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st,
                        const PeerKeys* peers = nullptr);
@@ -125,22 +136,26 @@ bool tf32_shape_ok(int64_t N, int D, int64_t K);
 bool tf32_search_splits(int64_t N, int64_t K);
 int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
                             int64_t* idx, int64_t* idx2, cudaStream_t st);
-int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2, cudaStream_t st);
-// unsharded search in any mode (AUTO already resolved): idx out; `scratch` = N int64 (keys / runner-up indices)
-int run_search(int mode, const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t* idx,
-               long long* scratch, cudaStream_t st);
+int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2,
+                       const float* e2max, cudaStream_t st);
+// unsharded search in any mode (AUTO already resolved): idx out; `scratch` = N int64 (keys / packed runner-up words).
+// tf32_refine: with `deferred` the exact re-evaluation of the top-2 pair is left to launch_quantize (pass it `scratch`
+// as idx2); *deferred says whether that is still owed.  Without it the stand-alone refine kernel runs here.
+int run_search(int mode, const float* z, const float* E, const float* e2, const float* e2max, int64_t N, int D, int64_t K,
+               int64_t* idx, long long* scratch, cudaStream_t st, int* deferred = nullptr);
 int launch_fill_keys(long long* keys, int64_t N, cudaStream_t st);
 int launch_keys_to_idx(const long long* keys, int64_t N, int64_t* idx, cudaStream_t st);
-int launch_quantize(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int64_t K,
+// idx2 / e2max given: fused exact re-evaluation of the tf32 top-2 pair (idx is then rewritten where the runner-up wins)
+int launch_quantize(const float* z, const float* E, int64_t* idx, int64_t N, int D, int64_t K,
                     int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st,
-                    const ShardPtrs* shards = nullptr);
+                    const ShardPtrs* shards = nullptr, const int64_t* idx2 = nullptr, const float* e2max = nullptr);
 int launch_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, int D, int64_t K, float beta,
                     float* loss, float* perplexity, cudaStream_t st);
 int launch_backward(const float* z, const float* E, const int64_t* idx, const int32_t* hist, const float* g_zq,
                     const float* g_loss, int64_t N, int D, int64_t K, int64_t k_offset, float beta,
                     int64_t n_global, float* dz, float* dE, void* ws, size_t ws_bytes, cudaStream_t st,
                     const RemoteGrad* remote = nullptr);
-size_t backward_workspace_bytes(int64_t N, int64_t K);
+size_t backward_workspace_bytes(int64_t N, int D, int64_t K);
 int launch_dz_from_zq(const float* z, const float* z_q, const float* g_zq, const float* g_loss, int64_t numel,
                       double inv_nd, float* dz, cudaStream_t st);
 int launch_cooccurrence(const int64_t* tokens, const int64_t* codes, int64_t N, int64_t V, int64_t K, int32_t* table,

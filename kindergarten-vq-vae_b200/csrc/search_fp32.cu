@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(F_THREADS) search_fp32_kernel(const float* __r
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float s = fmaf(-2.f, acc[i][j], en);
-          if (s < best[i]) { best[i] = s; bidx[i] = (uint32_t)(col + k_offset); }
+          // torch.argmin order: a NaN score wins outright (`!(s >= best)` fires for it), the first NaN is never replaced
+          if (!(s >= best[i]) && best[i] == best[i]) { best[i] = s; bidx[i] = (uint32_t)(col + k_offset); }
         }
       }
     }

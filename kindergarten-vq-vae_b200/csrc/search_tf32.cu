@@ -141,17 +141,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// L2 eviction-priority policies for the TMA loads: codebook tiles are re-read by every CTA pair on every sweep
+// (keep them: evict_last), latent tiles are read exactly once (evict_first), so the 1 GiB latent stream does not push
+// the 64 MiB codebook out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 template <int CG>
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint64_t policy) {
   if constexpr (CG == 1) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
   } else {  // data lands in this CTA, completion bytes are signalled on the LEADER CTA's barrier
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
   }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -214,18 +228,20 @@ __device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
         "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
       :: "memory");
 }
+// NaN-propagating minima (FMNMX3.NAN / FMNMX.NAN): a NaN score must surface in the batch minimum, because
+// torch.argmin (models/shelgon3/VectorQuantizer.py:65) treats NaN as the smallest value.
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
   float r;
-  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
-
-// One batch of 32 accumulator columns for one latent row: scores, their minimum by an FMNMX3 tree, and -- only when
-// the minimum beats the running best (rare after the first tiles) -- a scan for the FIRST column attaining it.
-// Equivalent to scanning the columns in increasing order with a strict '<': lowest index wins ties, NaN never wins.
-__device__ __forceinline__ void argmin_batch(const uint32_t (&acc)[32], const float4* __restrict__ e2v, uint32_t col_base,
-                                             float& best, uint32_t& bidx) {
-  float s[32];
+__device__ __forceinline__ float fmin2(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+// scores of one batch of 32 accumulator columns and their minimum (NaN if any score is NaN)
+__device__ __forceinline__ float batch_scores(const uint32_t (&acc)[32], const float4* __restrict__ e2v, float (&s)[32]) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     const float4 en = __ldg(e2v + j4);
@@ -237,21 +253,43 @@ __device__ __forceinline__ void argmin_batch(const uint32_t (&acc)[32], const fl
   float t[11];
 #pragma unroll
   for (int i = 0; i < 10; ++i) t[i] = fmin3(s[3 * i], s[3 * i + 1], s[3 * i + 2]);
-  t[10] = fminf(s[30], s[31]);
+  t[10] = fmin2(s[30], s[31]);
   const float u0 = fmin3(t[0], t[1], t[2]), u1 = fmin3(t[3], t[4], t[5]), u2 = fmin3(t[6], t[7], t[8]);
-  const float u3 = fminf(t[9], t[10]);
-  const float m = fminf(fmin3(u0, u1, u2), u3);
-  if (m < best) {
-    best = m;
-    int j = 31;
+  const float u3 = fmin2(t[9], t[10]);
+  return fmin2(fmin3(u0, u1, u2), u3);
+}
+// first column of the batch attaining the minimum m (first NaN column when m is NaN)
+__device__ __forceinline__ int first_column_of(const float (&s)[32], float m) {
+  int j = 31;
+  if (m == m) {
 #pragma unroll
     for (int jj = 30; jj >= 0; --jj) j = (s[jj] == m) ? jj : j;
-    bidx = col_base + (uint32_t)j;
+  } else {
+#pragma unroll
+    for (int jj = 30; jj >= 0; --jj) j = (s[jj] != s[jj]) ? jj : j;
+  }
+  return j;
+}
+
+// One batch of 32 accumulator columns for one latent row: scores, their minimum by an FMNMX3 tree, and -- only when
+// the minimum beats the running best (rare after the first tiles) -- a scan for the FIRST column attaining it.
+// Equivalent to torch.argmin over the columns in increasing order: lowest index wins ties, the first NaN wins outright
+// (the test `!(m >= best)` also fires for a NaN minimum; a NaN best is never replaced).
+__device__ __forceinline__ void argmin_batch(const uint32_t (&acc)[32], const float4* __restrict__ e2v, uint32_t col_base,
+                                             float& best, uint32_t& bidx) {
+  float s[32];
+  const float m = batch_scores(acc, e2v, s);
+  if (!(m >= best)) {
+    if (best == best) {
+      best = m;
+      bidx = col_base + (uint32_t)first_column_of(s, m);
+    }
   }
 }
 
 // Running top-2 of one latent row.  The overall runner-up is either the best of some OTHER 32-column batch (ov, oi)
 // or the second best inside the batch that holds the winner (b2v, b2i); both are maintained in the rare paths only.
+// Once the winner is a NaN nothing else is tracked (the runner-up is irrelevant: the exact pass keeps a NaN winner).
 struct Top2 {
   float bv, b2v, ov;
   uint32_t bi, b2i, oi;
@@ -259,40 +297,25 @@ struct Top2 {
 __device__ __forceinline__ void argmin_batch_top2(const uint32_t (&acc)[32], const float4* __restrict__ e2v,
                                                   uint32_t col_base, Top2& t) {
   float s[32];
+  const float m = batch_scores(acc, e2v, s);
+  if (!(m >= t.bv)) {
+    if (t.bv == t.bv) {
+      // the previous winner becomes a candidate of the "other batches" slot (its own batch's runner-up cannot beat it)
+      if (t.bv < t.ov || (t.bv == t.ov && t.bi < t.oi)) { t.ov = t.bv; t.oi = t.bi; }
+      const int j = first_column_of(s, m);
+      t.bv = m;
+      t.bi = col_base + (uint32_t)j;
+      float r = INFINITY;
+      int rj = 0;
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 en = __ldg(e2v + j4);
-    s[j4 * 4 + 0] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 0]), en.x);
-    s[j4 * 4 + 1] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 1]), en.y);
-    s[j4 * 4 + 2] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 2]), en.z);
-    s[j4 * 4 + 3] = fmaf(-2.f, __uint_as_float(acc[j4 * 4 + 3]), en.w);
-  }
-  float u[11];
-#pragma unroll
-  for (int i = 0; i < 10; ++i) u[i] = fmin3(s[3 * i], s[3 * i + 1], s[3 * i + 2]);
-  u[10] = fminf(s[30], s[31]);
-  const float m = fminf(fmin3(fmin3(u[0], u[1], u[2]), fmin3(u[3], u[4], u[5]), fmin3(u[6], u[7], u[8])), fminf(u[9], u[10]));
-  if (m < t.bv) {
-    // the previous winner becomes a candidate of the "other batches" slot (its own batch's runner-up cannot beat it)
-    if (t.bv < t.ov || (t.bv == t.ov && t.bi < t.oi)) { t.ov = t.bv; t.oi = t.bi; }
-    int j = 31;
-#pragma unroll
-    for (int jj = 30; jj >= 0; --jj) j = (s[jj] == m) ? jj : j;
-    t.bv = m;
-    t.bi = col_base + (uint32_t)j;
-    float r = INFINITY;
-    int rj = 0;
-#pragma unroll
-    for (int jj = 31; jj >= 0; --jj)
-      if (jj != j && s[jj] <= r) { r = s[jj]; rj = jj; }     // '<=' while walking down: first index wins ties
-    t.b2v = r;
-    t.b2i = col_base + (uint32_t)rj;
+      for (int jj = 31; jj >= 0; --jj)
+        if (jj != j && s[jj] <= r) { r = s[jj]; rj = jj; }     // '<=' while walking down: first index wins ties
+      t.b2v = r;
+      t.b2i = col_base + (uint32_t)rj;
+    }
   } else if (m < t.ov) {
-    int j = 31;
-#pragma unroll
-    for (int jj = 30; jj >= 0; --jj) j = (s[jj] == m) ? jj : j;
     t.ov = m;
-    t.oi = col_base + (uint32_t)j;
+    t.oi = col_base + (uint32_t)first_column_of(s, m);
   }
 }
 
@@ -370,6 +393,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
     // =========================== TMA producer (every CTA) ===========================
     // The whole warp walks the loop (warp-uniform control flow); one elected lane issues the copies.
     uint32_t stage = 0, phase = 0, a_phase = 0;
+    const uint64_t pol_z = l2_policy_evict_first(), pol_e = l2_policy_evict_last();
     // completion bytes of both CTAs are counted on the leader's barriers
     const uint32_t a_full_sig = (CG == 2) ? map_to_cta(bar_a_full, 0) : bar_a_full;
     for (int64_t item = first_item; item < p.n_items; item += item_stride) {
@@ -383,7 +407,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
         if (elect_one()) {
           if (leader) mbar_expect_tx(bar_a_full, a_bytes * CG);
           for (int kb = 0; kb < p.num_kblocks; ++kb)
-            tma_load_2d<CG>(a_region + kb * A_KBLOCK_BYTES, &tmap_z, kb * BLOCK_K, m0, a_full_sig);
+            tma_load_2d<CG>(a_region + kb * A_KBLOCK_BYTES, &tmap_z, kb * BLOCK_K, m0, a_full_sig, pol_z);
         }
         __syncwarp();
         a_phase ^= 1;
@@ -398,10 +422,10 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
             const uint32_t full_sig = (CG == 2) ? map_to_cta(full_own, 0) : full_own;
             if (leader) mbar_expect_tx(full_own, stage_bytes * CG);
             if (!p.resident) {
-              tma_load_2d<CG>(sbase, &tmap_z, kb * BLOCK_K, m0, full_sig);
-              tma_load_2d<CG>(sbase + A_KBLOCK_BYTES, &tmap_e, kb * BLOCK_K, n0, full_sig);
+              tma_load_2d<CG>(sbase, &tmap_z, kb * BLOCK_K, m0, full_sig, pol_z);
+              tma_load_2d<CG>(sbase + A_KBLOCK_BYTES, &tmap_e, kb * BLOCK_K, n0, full_sig, pol_e);
             } else {
-              tma_load_2d<CG>(sbase, &tmap_e, kb * BLOCK_K, n0, full_sig);
+              tma_load_2d<CG>(sbase, &tmap_e, kb * BLOCK_K, n0, full_sig, pol_e);
             }
           }
           __syncwarp();
@@ -531,7 +555,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
           ov2 = merge_val[row_in_tile];
           oi2 = merge_idx[row_in_tile];
         }
-        if (ov < bv || (ov == bv && oi < bi)) {
+        if (argmin_better(ov, oi, bv, bi)) {
           // the other half holds the winner: runner-up = better of (our winner, their runner-up)
           if constexpr (TOP2) {
             const bool theirs = (ov2 < bv) || (ov2 == bv && oi2 < bi);
@@ -544,7 +568,14 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
         }
         const int64_t row = (m_group * CG + cta_rank) * BLOCK_M + row_in_tile;
         if constexpr (TOP2) {
-          if (row < p.N && p.idx2) p.idx2[row] = (int64_t)((sv < INFINITY ? si : bi) + p.k_offset);
+          // runner-up index in the low word, the tf32 score gap (runner-up - winner; +inf when there is no runner-up,
+          // NaN when the winner is a NaN) in the high word: the exact pass only re-evaluates pairs whose gap is within
+          // the tf32 error bound of the row
+          if (row < p.N && p.idx2) {
+            const uint32_t ri = (sv < INFINITY ? si : bi) + (uint32_t)p.k_offset;
+            const float gap = (sv < INFINITY) ? (sv - bv) : ((bv == bv) ? INFINITY : bv);
+            p.idx2[row] = (int64_t)(((unsigned long long)__float_as_uint(gap) << 32) | (unsigned long long)ri);
+          }
         }
         if (row < p.N) {
           const uint32_t gi = (uint32_t)(bi + p.k_offset);
@@ -691,7 +722,8 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
     count_launch();
     KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG, TOP2>, mz, me, p));
   }
-  if (p.peers.n == 0 && p.use_atomic && idx && !keys_accumulate) return launch_keys_to_idx(keys, N, idx, st);
+  // (also when the caller accumulates into its own key buffer: idx then reflects the merged keys, like the fp32 path)
+  if (p.peers.n == 0 && p.use_atomic && idx) return launch_keys_to_idx(keys, N, idx, st);
   return KVQ_OK;
 }
 

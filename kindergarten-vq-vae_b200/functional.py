@@ -142,10 +142,15 @@ def vq_backward(z: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, hist: Optio
                 g_zq: Optional[torch.Tensor] = None, g_loss: Optional[torch.Tensor] = None, need_dz: bool = True,
                 need_dE: bool = True, k_offset: int = 0, n_global: Optional[int] = None,
                 ws: Optional[torch.Tensor] = None):
-    """Backward (autograd of VectorQuantizer.py:72-80).  Returns (dz or None, dE or None)."""
+    """Backward (autograd of VectorQuantizer.py:72-80).  Returns (dz or None, dE or None).
+
+    With a code shard (`k_offset` / E covering part of the codebook) ask for dz and dE in separate calls: the dE pass
+    visits only the latents whose code lies in the shard, the dz-only call passes g_zq through for the others."""
     _req(z, "z", torch.float32); _req(E, "E", torch.float32); _req(idx, "idx", torch.int64)
     N, D = z.shape
     K = E.shape[0]
+    if need_dz and need_dE and k_offset != 0:
+        raise RuntimeError("vq_backward: with a code shard (k_offset != 0) request dz and dE in separate calls")
     if g_zq is not None:
         _req(g_zq, "g_zq", torch.float32)
     if g_loss is not None:

@@ -52,8 +52,8 @@ def kmeans2(data: torch.Tensor, k: Union[int, torch.Tensor], iter: int = 10, min
     hist = torch.empty(K, dtype=torch.int32, device=data.device)
     nxt = torch.empty_like(cent)
     labels = torch.zeros(N, dtype=torch.int64, device=data.device)
-    stream = torch.cuda.current_stream().cuda_stream
     with torch.cuda.device(data.device):
+        stream = torch.cuda.current_stream().cuda_stream      # the stream of data's device, not of the caller's
         for _ in range(iter):
             labels, _ = F.search(data, cent, mode=search, ws=ws)
             check(lib.kvq_histogram(labels.data_ptr(), N, K, 0, hist.data_ptr(), stream), "kvq_histogram")

@@ -26,6 +26,12 @@ def _seed(seed: Optional[int]) -> int:
     return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _counter[0]) & 0xFFFFFFFFFFFFFFFF
 
 
+def _require_integer(tensor: Tensor, who: str) -> None:
+    # the kernels work on int64 token ids; a float tensor would be silently truncated by the round trip
+    if tensor.is_floating_point() or tensor.is_complex() or tensor.dtype == torch.bool:
+        raise RuntimeError(f"{who} (kvq) corrupts integer token-id tensors; got dtype {tensor.dtype}")
+
+
 def replace_pct_rand_values(tensor: Tensor, percentage: float, rand_int_low: int, rand_int_high: int,
                             seed: Optional[int] = None) -> Tensor:
     """Replace exactly int(numel*percentage) randomly chosen elements by uniform ints in [low, high)."""
@@ -33,6 +39,7 @@ def replace_pct_rand_values(tensor: Tensor, percentage: float, rand_int_low: int
         return tensor
     if tensor.get_device() < 0:
         raise RuntimeError("replace_pct_rand_values expects a CUDA tensor (as the reference does)")
+    _require_integer(tensor, "replace_pct_rand_values")
     src = tensor.to(torch.int64).contiguous()
     out = torch.empty_like(src)
     with torch.cuda.device(src.device):
@@ -54,6 +61,7 @@ def change_percentage_of_elements(tensor: Tensor, dim, percentage, min, max, see
         raise RuntimeError("change_percentage_of_elements expects a CUDA tensor (as the reference does)")
     if tensor.dim() != 2:
         raise RuntimeError("change_percentage_of_elements expects a 2-D tensor")
+    _require_integer(tensor, "change_percentage_of_elements")
     src = tensor.to(torch.int64).contiguous()
     out = torch.empty_like(src)
     R, C = src.shape
