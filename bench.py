@@ -367,9 +367,25 @@ def run_kvq(args):
                       "tolerance": "oracle.vq_oracle.tf32_tolerance: 2^-9 |z_i| max_k|E_k| + 4 ulp32(d) on the fp64 "
                                    "squared-distance gap (DESIGN.md section 3)"}
             del d, zs, Ed
-        if world > 1:
-            # batch-sharded run: the all-reduced dE against an fp64 sum of every rank's contribution on sampled codes
-            pass
+
+    # ---- batch-sharded run: the all-reduced dE of the timed step against an fp64 sum of every rank's contribution
+    dp_check = None
+    if world > 1 and not args.no_parity:
+        with torch.no_grad():
+            codes = torch.arange(0, K, K // 64, device=dev)[:64]
+            c2 = 2.0 * BETA / (float(n_rows) * world * D)              # g_loss = 1, normalised by the GLOBAL N * D
+            contrib = torch.zeros(codes.numel(), D, dtype=torch.float64, device=dev)
+            for j, k in enumerate(codes.tolist()):
+                rows_k = (idx_timed == k).nonzero().flatten()
+                if rows_k.numel():
+                    contrib[j] = (E[k].double()[None, :] - z[rows_k].double()).sum(0) * c2
+            dist.all_reduce(contrib, op=dist.ReduceOp.SUM)
+            err = float((dE_timed[codes].double() - contrib).abs().max())
+            scale = float(contrib.abs().max())
+            dp_check = {"codes_checked": int(codes.numel()), "max_abs_err": err, "max_abs_ref": scale,
+                        "rel_err": err / max(scale, 1e-30), "tolerance_rel": 1e-5,
+                        "what": "all-reduced dE rows of the last timed step vs an fp64 sum of all ranks' contributions"}
+            assert dp_check["rel_err"] <= 1e-5, dp_check
 
     # ---- plain tf32 search (no exact re-evaluation) timed beside the default, same inputs, outside the headline
     refine = None
@@ -394,6 +410,15 @@ def run_kvq(args):
     e2e = None
     if not args.no_e2e:
         e2e = measure_e2e(torch, dist, F, vq, z, gz, E, dev, world, args)
+        e2e["bare_copy_ceiling"] = measure_copy_ceiling(torch, dist, dev, world, e2e["h2d_bytes_per_step"],
+                                                        e2e["d2h_bytes_per_step"], n_rows)
+
+    # ---- BASELINE.json configs[3]: K = 2^20 codebook sharded over the ranks, latents replicated ---------------------
+    kshard = None
+    if world > 1 and not args.no_kshard:
+        del vq
+        torch.cuda.empty_cache()
+        kshard = measure_kshard(torch, dist, kvq, lib, _lib, dev, rank, world, args)
 
     # ---- rooflines -----------------------------------------------------------------------------------------
     pk = peaks()
@@ -489,13 +514,119 @@ def run_kvq(args):
                        "codebook_init": "data-scale: N(0,1) rows + 0.1 noise"},
             "roofline": roof, "roofline_other_kernels": others, "kernel_ms": prof,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "host_placement": numa, "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp),
+            "kshard": kshard, "dp_dE_check": dp_check, "host_placement": numa, "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp),
             "search_mode": search_mode, "index_parity": parity, "plain_tf32_beside": refine, "reference_cuda": ref_cuda,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+KSHARD_K = 1 << 20
+
+
+def measure_copy_ceiling(torch, dist, dev, world, h2d_bytes, d2h_bytes, n_rows):
+    """Bare pinned-memory copies of exactly the bytes one end-to-end step moves, both directions concurrently on two
+    streams, all ranks at once: the ceiling the host side of this box puts on the end-to-end number."""
+    nh, nd = h2d_bytes // 4, d2h_bytes // 4
+    src_h = torch.empty(nh, dtype=torch.float32, pin_memory=True); dst_d = torch.empty(nh, dtype=torch.float32, device=dev)
+    src_d = torch.empty(nd, dtype=torch.float32, device=dev); dst_h = torch.empty(nd, dtype=torch.float32, pin_memory=True)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def once():
+        with torch.cuda.stream(s_in):
+            dst_d.copy_(src_h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            dst_h.copy_(src_d, non_blocking=True)
+        s_in.synchronize(); s_out.synchronize()
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        once()
+    if world > 1:
+        dist.barrier()
+    dt = (time.perf_counter() - t0) / 3
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {"ms_per_step": dt * 1e3, "latents_per_s_ceiling": n_rows * world / dt,
+            "h2d_gbs_per_gpu": h2d_bytes / dt / 1e9, "d2h_gbs_per_gpu": d2h_bytes / dt / 1e9,
+            "what": "cudaMemcpyAsync of the step's H2D and D2H bytes from/to pinned memory on two streams, no compute, "
+                    "all ranks concurrently (max over ranks)"}
+
+
+def measure_kshard(torch, dist, kvq, lib, _lib, dev, rank, world, args):
+    """BASELINE.json configs[3]: K = 2^20 codes (D = 256) sharded over the ranks, N = 2^20 latents replicated; forward +
+    backward of CodebookShardedVectorQuantizer with its default exchange (fused NVLink peer-memory argmin + peer gather when
+    symmetric memory is available).  Index parity on sampled rows against oracle.kshard_merge."""
+    Kt, n_rows = KSHARD_K, N_PER_GPU
+    gen = torch.Generator(device=dev).manual_seed(SEED + 7)         # same latents on every rank
+    z = torch.randn(n_rows, D, device=dev, generator=gen)
+    gz = torch.randn(n_rows, D, device=dev, generator=gen)
+    vq = kvq.CodebookShardedVectorQuantizer(Kt, D, BETA).to(dev)
+
+    def shard_values(r):
+        g = torch.Generator(device=dev).manual_seed(SEED + 100 + r)
+        return torch.randn(vq.k_per, D, device=dev, generator=g) * 1.005
+    with torch.no_grad():
+        vq.embedding.weight.copy_(shard_values(rank))
+    z3 = z.view(n_rows // 64, 64, D).requires_grad_(True)
+    gz3 = gz.view_as(z3)
+    one = torch.ones((), device=dev)
+    last = {}
+
+    def step():
+        z3.grad = None
+        vq.embedding.weight.grad = None
+        loss, z_q, perp, _, idx = vq.forward(z3, dev)
+        torch.autograd.backward([loss, z_q], [one, gz3])
+        last["idx"], last["loss"], last["perp"] = idx, loss, perp
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    lib.kvq_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.kshard_steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    lib.kvq_profile_enable(0)
+    ms = (ctypes.c_double * 6)(); cnt = (ctypes.c_int * 6)()
+    _lib.check(lib.kvq_profile_collect(ms, cnt, 6), "kvq_profile_collect")
+    search_ms = ms[1] / cnt[1] if cnt[1] else None
+    t = torch.tensor([e0.elapsed_time(e1) / args.kshard_steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())
+    out = {"workload": f"codebook-sharded VQ fwd+bwd, K={Kt} over {world} ranks ({vq.k_per} codes each), N={n_rows} latents "
+                       f"replicated, D={D}",
+           "K": Kt, "N": n_rows, "D": D, "ranks": world, "exchange": vq.exchange, "steps": args.kshard_steps,
+           "ms_per_step": ms_step, "latents_per_s": n_rows / (ms_step * 1e-3),
+           "aggregate_tflops_whole_step": 2.0 * n_rows * Kt * D / (ms_step * 1e-3) / 1e12,
+           "search_ms_per_rank": search_ms,
+           "search_tflops_per_rank": (2.0 * n_rows * vq.k_per * D / (search_ms * 1e-3) / 1e12) if search_ms else None,
+           "loss": float(last["loss"].detach()), "perplexity": float(last["perp"])}
+    if rank == 0 and not args.no_parity:
+        from oracle import vq_oracle as O              # checker only
+        with torch.no_grad():
+            rows = torch.arange(0, n_rows, n_rows // 1024, device=dev)[:1024]
+            E_full = torch.cat([shard_values(r) for r in range(world)])[:Kt].cpu()
+            zs = z[rows].cpu()
+            ours = last["idx"].reshape(-1)[rows].cpu()
+            t0 = time.perf_counter()
+            ref = O.kshard_merge(zs, E_full, world)
+            par = O.index_parity(ours, ref, zs, E_full)
+            out["index_parity_vs_oracle_kshard_merge"] = {"rows_checked": int(rows.numel()), "raw_mismatch": par.raw_mismatch,
+                                                          "unexcused": par.unexcused,
+                                                          "max_gap_over_tolerance": par.max_gap_over_tol,
+                                                          "oracle_seconds": time.perf_counter() - t0}
+            assert par.unexcused == 0, par
+    return out
 
 
 def measure_e2e(torch, dist, F, vq, z, gz, E, dev, world, args):
@@ -554,6 +685,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-side", action="store_true")
     ap.add_argument("--no-refcuda", action="store_true")
+    ap.add_argument("--no-kshard", action="store_true")
+    ap.add_argument("--kshard-steps", type=int, default=4)
     ap.add_argument("--chunk-rows", type=int, default=75776)  # 4 full waves of 74 CTA pairs x 256 rows
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "kvq":

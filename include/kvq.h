@@ -139,6 +139,12 @@ int kvq_forward(const float* z, const float* E, int64_t N, int D, int64_t K, flo
                 float* z_q, int64_t* idx, float* loss, float* perplexity, int32_t* hist,
                 void* workspace, size_t workspace_bytes, kvq_stream_t stream);
 
+/* kvq_forward without the finalisation, for a batch sharded over ranks: this rank's rows are searched and gathered, and
+ * the two quantities that span ranks are left as partials -- sq_sum (1 double, overwritten) and hist (K int32,
+ * overwritten).  The caller SUM-all-reduces them and calls kvq_finalize with the global latent count. */
+int kvq_forward_partials(const float* z, const float* E, int64_t N, int D, int64_t K, int mode, float* z_q, int64_t* idx,
+                         double* sq_sum, int32_t* hist, void* workspace, size_t workspace_bytes, kvq_stream_t stream);
+
 /* Backward of the layer (what autograd derives from VectorQuantizer.py:72-80):
  *   dz[i]  = g_zq[i] + g_loss * 2 (z_i - q_i) / (n_global D)
  *   dE[k]  = g_loss * beta * 2 / (n_global D) * sum_{i: idx_i = k} (q_i - z_i)      dense, exact zeros elsewhere
@@ -190,6 +196,21 @@ int kvq_onehot(const int64_t* idx, int64_t N, int64_t K, float* out, kvq_stream_
 /* Token accuracy.  common/metrics.py:8-36.  a, b are (B,S) int64; acc is 1 float, per_sentence is B floats. */
 int kvq_seq_acc(const int64_t* a, const int64_t* b, int64_t B, int64_t S, float* acc, float* per_sentence,
                 kvq_stream_t stream);
+
+/* Reconstruction loss of the shelgon3 train step, fused (models/shelgon3/Trainer.py:94-101): one pass over the logits
+ * (B*S rows x V) instead of a dense one-hot + log_softmax + kl_div + softmax + argmax + seq_acc chain.
+ *   loss             = kl_div(log_softmax(logits), one_hot(ids, V), "batchmean") = sum_r (logsumexp_r - x_r[id_r]) / (B*S)
+ *   recon_ids[r]     = argmax_j logits[r, j]  (= argmax(softmax(.)); first index on ties; B*S int64)
+ *   acc, acc_per_sentence = common/metrics.py:8-36 of (recon_ids, ids): 1 float and B floats
+ *   row_lse          = logsumexp of every row (B*S floats), kept for the backward
+ * workspace: kvq_recon_workspace_bytes(B, S) bytes. */
+size_t kvq_recon_workspace_bytes(int64_t B, int64_t S);
+int kvq_recon_loss_forward(const float* logits, const int64_t* ids, int64_t B, int64_t S, int64_t V, float* loss,
+                           int64_t* recon_ids, float* acc, float* acc_per_sentence, float* row_lse, void* workspace,
+                           size_t workspace_bytes, kvq_stream_t stream);
+/* dlogits[r, j] = g_loss * (softmax(logits)[r, j] - [j == ids[r]]) / (B*S); g_loss is a DEVICE scalar (NULL = 1). */
+int kvq_recon_loss_backward(const float* logits, const int64_t* ids, const float* row_lse, const float* g_loss, int64_t B,
+                            int64_t S, int64_t V, float* dlogits, kvq_stream_t stream);
 
 /* Token-id corruption helpers.  common/tensor_utils.py:13-49 and :52-87, with a counter-based device RNG
  * (seeded; the reference uses the host RNG, so parity is distributional: exact counts, value ranges).

@@ -37,6 +37,7 @@ SIGNATURES = {
     "kvq_quantize": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, c_int64, c_int, _P, _P, _P, _P]),
     "kvq_finalize": (c_int, [_P, _P, c_int64, c_int, c_int64, c_float, _P, _P, _P]),
     "kvq_forward": (c_int, [_P, _P, c_int64, c_int, c_int64, c_float, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "kvq_forward_partials": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "kvq_backward": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_int64, c_float, c_int64, _P, _P,
                              _P, c_size_t, _P]),
     "kvq_backward_peers": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_float, c_int64, _P, _P, _P, c_int,
@@ -47,6 +48,9 @@ SIGNATURES = {
     "kvq_kmeans_update": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, _P, _P, _P, c_size_t, _P]),
     "kvq_onehot": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "kvq_seq_acc": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P]),
+    "kvq_recon_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "kvq_recon_loss_forward": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "kvq_recon_loss_backward": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P]),
     "kvq_replace_pct_rand_values": (c_int, [_P, c_int64, c_double, c_int64, c_int64, c_uint64, _P, _P]),
     "kvq_change_percentage_of_elements": (c_int, [_P, c_int64, c_int64, c_int, c_double, c_int64, c_int64, c_uint64,
                                                   _P, _P]),

@@ -278,33 +278,52 @@ int kvq_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, in
   return launch_finalize(sq_sum, hist, n_global, D, K, beta, loss, perplexity, (cudaStream_t)stream);
 }
 
-int kvq_forward(const float* z, const float* E, int64_t N, int D, int64_t K, float beta, int mode, float* z_q,
-                int64_t* idx, float* loss, float* perplexity, int32_t* hist, void* ws, size_t ws_bytes,
-                kvq_stream_t stream) {
+// norms -> search (-> fused exact re-evaluation) -> gather / straight-through / partial sums.  sq_sum and hist are overwritten.
+static int forward_partials(const char* who, const float* z, const float* E, int64_t N, int D, int64_t K, int mode,
+                            float* z_q, int64_t* idx, double* sq_sum, int32_t* hist, void* ws, size_t ws_bytes,
+                            cudaStream_t st, FwdWs* carved) {
   int rc = check_device(); if (rc) return rc;
-  rc = check_shape("kvq_forward", N, D, K); if (rc) return rc;
-  KVQ_REQUIRE(N >= 1, KVQ_ERR_ARG, "kvq_forward: N must be >= 1");
-  KVQ_REQUIRE(z && E && z_q && idx && loss && perplexity && hist && ws, KVQ_ERR_ARG, "kvq_forward: null pointer");
-  KVQ_REQUIRE(((uintptr_t)ws & 255) == 0, KVQ_ERR_WORKSPACE, "kvq_forward: workspace must be 256-byte aligned");
+  rc = check_shape(who, N, D, K); if (rc) return rc;
+  KVQ_REQUIRE(N >= 1, KVQ_ERR_ARG, "%s: N must be >= 1", who);
+  KVQ_REQUIRE(z && E && z_q && idx && hist && ws, KVQ_ERR_ARG, "%s: null pointer", who);
+  KVQ_REQUIRE(((uintptr_t)ws & 255) == 0, KVQ_ERR_WORKSPACE, "%s: workspace must be 256-byte aligned", who);
   FwdWs w = carve_forward(ws, N, K);
-  KVQ_REQUIRE(ws_bytes >= w.bytes, KVQ_ERR_WORKSPACE, "kvq_forward: workspace %zu < %zu bytes", ws_bytes, w.bytes);
+  KVQ_REQUIRE(ws_bytes >= w.bytes, KVQ_ERR_WORKSPACE, "%s: workspace %zu < %zu bytes", who, ws_bytes, w.bytes);
+  if (!sq_sum) sq_sum = w.sq_sum;
   int m; rc = resolve_mode(mode, N, D, K, &m); if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   { ProfScope ps(KVQ_PROF_NORMS, st); rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st, w.e2max); }
   if (rc) return rc;
   int deferred = 0;   // tf32_refine: the exact top-2 re-evaluation rides along in the gather kernel
   rc = run_search(m, z, E, w.e2, w.e2max, N, D, K, idx, w.keys, st, &deferred);
   if (rc) return rc;
-  KVQ_CUDA(cudaMemsetAsync(w.sq_sum, 0, sizeof(double), st));
+  KVQ_CUDA(cudaMemsetAsync(sq_sum, 0, sizeof(double), st));
   KVQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int32_t), st));
   {
     ProfScope ps(KVQ_PROF_QUANTIZE, st);
-    rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, w.sq_sum, hist, st, nullptr,
+    rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, sq_sum, hist, st, nullptr,
                          deferred ? reinterpret_cast<const int64_t*>(w.keys) : nullptr, deferred ? w.e2max : nullptr);
   }
+  if (carved) *carved = w;
+  return rc;
+}
+
+int kvq_forward(const float* z, const float* E, int64_t N, int D, int64_t K, float beta, int mode, float* z_q,
+                int64_t* idx, float* loss, float* perplexity, int32_t* hist, void* ws, size_t ws_bytes,
+                kvq_stream_t stream) {
+  KVQ_REQUIRE(loss && perplexity, KVQ_ERR_ARG, "kvq_forward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  FwdWs w;
+  int rc = forward_partials("kvq_forward", z, E, N, D, K, mode, z_q, idx, nullptr, hist, ws, ws_bytes, st, &w);
   if (rc) return rc;
   ProfScope ps(KVQ_PROF_FINALIZE, st);
   return launch_finalize(w.sq_sum, hist, N, D, K, beta, loss, perplexity, st);
+}
+
+int kvq_forward_partials(const float* z, const float* E, int64_t N, int D, int64_t K, int mode, float* z_q, int64_t* idx,
+                         double* sq_sum, int32_t* hist, void* ws, size_t ws_bytes, kvq_stream_t stream) {
+  KVQ_REQUIRE(sq_sum, KVQ_ERR_ARG, "kvq_forward_partials: null pointer");
+  return forward_partials("kvq_forward_partials", z, E, N, D, K, mode, z_q, idx, sq_sum, hist, ws, ws_bytes,
+                          (cudaStream_t)stream, nullptr);
 }
 
 int kvq_backward(const float* z, const float* E, const int64_t* idx, const int32_t* hist, const float* g_zq,

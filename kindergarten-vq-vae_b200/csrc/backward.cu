@@ -26,7 +26,7 @@ namespace kvq {
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;          // per thread -> 4096 per block
-constexpr int SCAN_SMALL_MAX = 131072;  // up to here one block scans the whole array (one launch instead of three)
+constexpr int SCAN_SMALL_MAX = 8192;    // up to here one block scans the whole array (one launch instead of three)
 
 // ---- 1. exclusive scan of an int32 array ---------------------------------------------------------
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const int32_t* __restrict__ hist, int64_t K,
@@ -122,22 +122,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int32_t*
   }
 }
 
-// short arrays: one block does the whole exclusive scan (each thread a contiguous run), one launch.
+// short arrays: one block does the whole exclusive scan in coalesced chunks of 1024, one launch.
 __global__ void __launch_bounds__(1024) scan_small_kernel(const int32_t* __restrict__ in, int n, int32_t* __restrict__ out,
                                                           int32_t* __restrict__ total) {
   __shared__ int32_t warp_tot[32];
-  const int per = (n + 1023) / 1024;
-  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
-  int32_t s = 0;
-  for (int i = lo; i < hi; ++i) s += in[i];
-  int32_t all;
-  int32_t run = block_exclusive_scan_1024(s, warp_tot, &all);
-  for (int i = lo; i < hi; ++i) {
-    const int32_t v = in[i];
-    out[i] = run;
-    run += v;
+  int32_t carry = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int32_t v = (i < n) ? in[i] : 0;
+    int32_t chunk_total;
+    const int32_t before = block_exclusive_scan_1024(v, warp_tot, &chunk_total);
+    if (i < n) out[i] = carry + before;
+    carry += chunk_total;
   }
-  if (threadIdx.x == 0) *total = all;
+  if (threadIdx.x == 0) *total = carry;
 }
 
 static inline int scan_blocks(int64_t n) { return (int)((n + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS)); }
@@ -263,40 +261,6 @@ __device__ __forceinline__ void red_add_sys(float4* addr, const float4& v) {
                ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__device__ __forceinline__ uint32_t seg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void seg_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void seg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool seg_mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Spin with a watchdog: a protocol bug traps (the launch reports an error) instead of hanging the GPU.
-__device__ __forceinline__ void seg_mbar_wait(uint32_t bar, uint32_t parity) {
-  if (seg_mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!seg_mbar_try(bar, parity)) {
-    if (((++spins) & 0xfffu) == 0 && clock64() - t0 > 4000000000ll) {  // ~2 s
-      printf("kvq segmented pass: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
-    }
-  }
-}
-// one row (bytes % 16 == 0, 16-byte aligned on both sides) global -> shared, completion counted on `bar`
-__device__ __forceinline__ void bulk_row_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 constexpr int SEG_WPB = 8;          // warps per block, each with its own ring
 constexpr int SEG_MAX_STAGES = 8;
 constexpr int SEG_BAR_BYTES = SEG_WPB * SEG_MAX_STAGES * 8;
@@ -381,9 +345,9 @@ __global__ void __launch_bounds__(SEG_WPB * 32, (VPL <= 4) ? 2 : 1) segmented_ke
   const uint32_t row_bytes = (uint32_t)D * 4u;
   const uint32_t stage_bytes = has_g ? 2u * row_bytes : row_bytes;
   // shared-memory map: [SEG_WPB x SEG_MAX_STAGES mbarriers][warp 0 ring][warp 1 ring]...
-  const uint32_t bars = seg_smem_u32(seg_smem) + (uint32_t)wib * SEG_MAX_STAGES * 8u;
+  const uint32_t bars = ring_smem_u32(seg_smem) + (uint32_t)wib * SEG_MAX_STAGES * 8u;
   uint8_t* ring = seg_smem + SEG_BAR_BYTES + (size_t)wib * stages * stage_bytes;
-  const uint32_t ring_u32 = seg_smem_u32(ring);
+  const uint32_t ring_u32 = ring_smem_u32(ring);
 
   if (lane == 0) { part.codes[warp_id * 2] = -1; part.codes[warp_id * 2 + 1] = -1; }
   const int spw = seg_slots_per_warp(total, n_warps);
@@ -394,7 +358,7 @@ __global__ void __launch_bounds__(SEG_WPB * 32, (VPL <= 4) ? 2 : 1) segmented_ke
   const int count = p1 - p0;
 
   if (lane == 0) {
-    for (int s = 0; s < stages; ++s) seg_mbar_init(bars + 8 * s, 1);
+    for (int s = 0; s < stages; ++s) ring_mbar_init(bars + 8 * s, 1);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // barrier init visible to the bulk-copy engine
   }
   __syncwarp();
@@ -419,7 +383,7 @@ __global__ void __launch_bounds__(SEG_WPB * 32, (VPL <= 4) ? 2 : 1) segmented_ke
       const int s = j % stages;
       const uint32_t bar = bars + 8 * s;
       const uint32_t dst = ring_u32 + (uint32_t)s * stage_bytes;
-      seg_mbar_expect_tx(bar, stage_bytes);
+      ring_mbar_expect_tx(bar, stage_bytes);
       bulk_row_g2s(dst, z + (int64_t)row * D, row_bytes, bar);
       if (has_g) bulk_row_g2s(dst + row_bytes, g_zq + (int64_t)row * D, row_bytes, bar);
     }
@@ -450,7 +414,7 @@ __global__ void __launch_bounds__(SEG_WPB * 32, (VPL <= 4) ? 2 : 1) segmented_ke
         }
       }
     }
-    seg_mbar_wait(bars + 8 * s, (uint32_t)((r / stages) & 1));
+    ring_mbar_wait(bars + 8 * s, (uint32_t)((r / stages) & 1));
     const float4* zs = reinterpret_cast<const float4*>(ring + (size_t)s * stage_bytes);
     const float4* gs = reinterpret_cast<const float4*>(ring + (size_t)s * stage_bytes + row_bytes);
     float4* out = (!MEAN && dz) ? reinterpret_cast<float4*>(dz + (int64_t)row * D) : nullptr;

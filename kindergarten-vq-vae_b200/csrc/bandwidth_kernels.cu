@@ -152,25 +152,20 @@ int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// gather + straight-through + squared-residual sum + usage histogram  (+ the exact top-2 re-evaluation, fused).
+// gather + straight-through + squared-residual sum + usage histogram.
 //
-// One warp owns 32 consecutive latents.  Lane j first reads idx[row0+j] (one coalesced 256-B read).  Rows are then
-// streamed four at a time: every lane issues 4*VPL 128-bit loads of z and 4*VPL of the codebook rows before the
-// first use (memory-level parallelism), z and z_q with streaming (L1::no_allocate) accesses, codebook rows through
-// the read-only path (they are re-used and L2 resident).  At the end the warp aggregates equal codes with
-// __match_any_sync, so a collapsed codebook costs one histogram atomic per warp instead of 32.
+// One warp owns 32 consecutive latents.  Lane j first reads idx[row0+j] (one coalesced 256-B read) and the
+// warp aggregates equal codes with __match_any_sync, so a collapsed codebook costs one histogram atomic per
+// warp instead of 32.  Rows are then streamed four at a time: every lane issues 4*VPL 128-bit loads of z and
+// 4*VPL of the codebook rows before the first use (memory-level parallelism), z and z_q with streaming
+// (L1::no_allocate) accesses, codebook rows through the read-only path (they are re-used and L2 resident).
+// This register-staged form serves the plain searches and the sharded codebooks (peer-mapped rows, skipped rows).
 //
-// REFINE instantiation (the layer's default search mode): the kernel already holds z[i] and E[a_i]; for the rows
-// whose tf32 top-2 gap is within the row's error bound (see above) it also fetches E[b_i], decides the pair in
-// float64, rewrites idx[i] when the runner-up wins and gathers the winner -- the separate pass over z that a
-// stand-alone refine kernel needs disappears.
-//
-// Algorithmic HBM bytes per latent: 4D (z) + 4D (E row) + 4D (z_q) + 8 (idx) [+ 8 idx2];  + 4K for the histogram.
+// Algorithmic HBM bytes per latent: 4D (z) + 4D (E row) + 4D (z_q) + 8 (idx);  + 4K for the histogram.
 // ------------------------------------------------------------------------------------------------
-template <int VPL, bool REFINE>
+template <int VPL>
 __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__ z, const float* __restrict__ E,
-                                                       int64_t* __restrict__ idx, const int64_t* __restrict__ idx2,
-                                                       const float* __restrict__ e2max_p, int64_t N, int D, int64_t K,
+                                                       const int64_t* __restrict__ idx, int64_t N, int D, int64_t K,
                                                        int64_t k_offset, int zero_skipped, float* __restrict__ z_q,
                                                        double* __restrict__ sq_sum, int32_t* __restrict__ hist,
                                                        const ShardPtrs shards) {
@@ -184,19 +179,15 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
   if (row0 < N) {
     const int64_t my_row = row0 + lane;
     int64_t code = -1;
-    int64_t code_b = -1;
-    float gap = INFINITY;
     if (my_row < N) {
       code = idx[my_row] - k_offset;
       if (code < 0 || code >= K) code = -1;
-      if constexpr (REFINE) {
-        const unsigned long long w = (unsigned long long)idx2[my_row];
-        code_b = (int64_t)(w & 0xffffffffull);
-        gap = __uint_as_float((unsigned)(w >> 32));
-        if (code_b >= K || code < 0) { code_b = code; gap = INFINITY; }
-      }
     }
-    const float e2max = REFINE ? *e2max_p : 0.f;
+    // histogram, aggregated over equal codes inside the warp
+    {
+      const unsigned peers = __match_any_sync(0xffffffffu, code);
+      if (code >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(hist + code, __popc(peers));
+    }
     const int rows_here = (int)min((int64_t)32, N - row0);
     for (int r0 = 0; r0 < rows_here; r0 += R) {
       float4 zv[R][VPL], ev[R][VPL];
@@ -222,61 +213,6 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
           }
         }
       }
-      if constexpr (REFINE) {
-        // |z_i|^2 of the R rows (independent shuffle trees), then the rows whose tf32 gap is inside the error bound
-        float z2[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          float t = 0.f;
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            t = fmaf(zv[r][v].x, zv[r][v].x, t); t = fmaf(zv[r][v].y, zv[r][v].y, t);
-            t = fmaf(zv[r][v].z, zv[r][v].z, t); t = fmaf(zv[r][v].w, zv[r][v].w, t);
-          }
-          z2[r] = t;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int r = 0; r < R; ++r) z2[r] += __shfl_xor_sync(0xffffffffu, z2[r], o);
-        int64_t cb[R];
-        bool close[R];
-        float4 bv[R][VPL];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          cb[r] = __shfl_sync(0xffffffffu, code_b, (r0 + r) & 31);
-          const float g = __shfl_sync(0xffffffffu, gap, (r0 + r) & 31);
-          close[r] = (r0 + r) < rows_here && cb[r] != c[r] && !(g > refine_threshold(z2[r], e2max));   // warp-uniform
-          if (close[r]) {
-            const float4* br = reinterpret_cast<const float4*>(E + cb[r] * (int64_t)D);
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-              const int col = lane + v * 32;
-              bv[r][v] = (col < nvec) ? __ldg(br + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (!close[r]) continue;
-          double da = 0.0, db = 0.0;
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            if (lane + v * 32 < nvec) {
-              da += sqdiff4(zv[r][v], ev[r][v]);
-              db += sqdiff4(zv[r][v], bv[r][v]);
-            }
-          }
-          da = warp_sum(da);
-          db = warp_sum(db);
-          if (db < da || (db == da && cb[r] < c[r])) {      // the runner-up is the exact winner
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) ev[r][v] = bv[r][v];
-            c[r] = cb[r];
-            if (lane == ((r0 + r) & 31)) { code = cb[r]; idx[my_row] = cb[r] + k_offset; }
-          }
-        }
-      }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const bool live = (r0 + r) < rows_here;
@@ -298,11 +234,6 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
         }
       }
     }
-    // histogram of the final codes, aggregated over equal codes inside the warp
-    {
-      const unsigned peers = __match_any_sync(0xffffffffu, code);
-      if (code >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(hist + code, __popc(peers));
-    }
   }
   // block reduction of the squared-residual sum: fp32 per lane (<= 32*VPL*4 terms), double above that
   __shared__ double part[8];
@@ -316,27 +247,216 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same pass for the layer's default search mode, with the exact top-2 re-evaluation fused in and the rows staged
+// through shared memory.  Persistent warps, each owning a contiguous range of latents; a lane-elected producer
+// bulk-copies (cp.async.bulk, mbarrier completion) row i of z and row a_i of the codebook into a per-warp ring,
+// `stages` rows ahead of the consumer.  Per row the consumer forms |z_i|^2, and only if the tf32 top-2 gap is inside
+// the row's error bound (see above) fetches E[b_i] and decides the pair in float64; it then gathers the winner,
+// writes z_q, accumulates the squared residual and records the final code (idx is rewritten where the runner-up won).
+// The separate pass over z that a stand-alone refine kernel needs disappears, and no registers hold bytes in flight.
+// ------------------------------------------------------------------------------------------------
+constexpr int QR_WPB = 8;
+constexpr int QR_MAX_STAGES = 8;
+constexpr int QR_BAR_BYTES = QR_WPB * QR_MAX_STAGES * 8;
+
+template <int VPL>
+__global__ void __launch_bounds__(QR_WPB * 32, (VPL <= 4) ? 2 : 1) quantize_refine_kernel(
+    const float* __restrict__ z, const float* __restrict__ E, int64_t* __restrict__ idx, const int64_t* __restrict__ idx2,
+    const float* __restrict__ e2max_p, int64_t N, int D, int64_t K, float* __restrict__ z_q, double* __restrict__ sq_sum,
+    int32_t* __restrict__ hist, int rows_per_warp, int stages) {
+  extern __shared__ __align__(128) uint8_t qr_smem[];
+  __shared__ double part[QR_WPB];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp_id = (int64_t)blockIdx.x * QR_WPB + wib;
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+  const uint32_t stage_bytes = 2u * row_bytes;
+  const uint32_t bars = ring_smem_u32(qr_smem) + (uint32_t)wib * QR_MAX_STAGES * 8u;
+  uint8_t* ring = qr_smem + QR_BAR_BYTES + (size_t)wib * stages * stage_bytes;
+  const uint32_t ring_u32 = ring_smem_u32(ring);
+  const int nvec = D >> 2;
+  float acc = 0.f;
+
+  const int64_t row0 = warp_id * rows_per_warp;
+  if (row0 < N) {
+    const int count = (int)min((int64_t)rows_per_warp, N - row0);
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) ring_mbar_init(bars + 8 * s, 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    const float e2max = *e2max_p;
+
+    // lane l holds winner / packed runner-up word of row 32*c + l; one chunk ahead is kept for the producer
+    auto load_a = [&](int base) -> int64_t {
+      int64_t a = 0;
+      if (base + lane < count) { a = idx[row0 + base + lane]; if (a < 0 || a >= K) a = 0; }
+      return a;
+    };
+    auto load_w = [&](int base) -> unsigned long long {
+      return (base + lane < count) ? (unsigned long long)idx2[row0 + base + lane] : 0ull;
+    };
+    int64_t cur_a = load_a(0), nxt_a = load_a(32);
+    unsigned long long cur_w = load_w(0), nxt_w = load_w(32);
+
+    auto issue = [&](int j, int consumer_chunk) {
+      const long long a_c = __shfl_sync(0xffffffffu, (long long)cur_a, j & 31);
+      const long long a_n = __shfl_sync(0xffffffffu, (long long)nxt_a, j & 31);
+      if (lane == 0) {
+        const long long a = ((j >> 5) == consumer_chunk) ? a_c : a_n;
+        const int s = j % stages;
+        const uint32_t bar = bars + 8 * s;
+        const uint32_t dst = ring_u32 + (uint32_t)s * stage_bytes;
+        ring_mbar_expect_tx(bar, stage_bytes);
+        bulk_row_g2s(dst, z + (row0 + j) * (int64_t)D, row_bytes, bar);
+        bulk_row_g2s(dst + row_bytes, E + a * (int64_t)D, row_bytes, bar);
+      }
+    };
+    for (int j = 0; j < stages && j < count; ++j) issue(j, 0);
+
+    int64_t final_code = cur_a;      // lane l: final code of row 32*chunk + l
+    for (int r = 0; r < count; ++r) {
+      const int s = r % stages;
+      const int64_t a = __shfl_sync(0xffffffffu, (long long)cur_a, r & 31);
+      const unsigned long long w = __shfl_sync(0xffffffffu, cur_w, r & 31);
+      int64_t b = (int64_t)(w & 0xffffffffull);
+      const float gap = __uint_as_float((unsigned)(w >> 32));
+      ring_mbar_wait(bars + 8 * s, (uint32_t)((r / stages) & 1));
+      const float4* zs = reinterpret_cast<const float4*>(ring + (size_t)s * stage_bytes);
+      const float4* es = reinterpret_cast<const float4*>(ring + (size_t)s * stage_bytes + row_bytes);
+      float4 zv[VPL], ev[VPL];
+      float z2 = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int col = lane + v * 32;
+        if (col < nvec) {
+          zv[v] = zs[col];
+          ev[v] = es[col];
+          z2 = fmaf(zv[v].x, zv[v].x, z2); z2 = fmaf(zv[v].y, zv[v].y, z2);
+          z2 = fmaf(zv[v].z, zv[v].z, z2); z2 = fmaf(zv[v].w, zv[v].w, z2);
+        } else {
+          zv[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          ev[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      __syncwarp();                                  // every lane has read stage s: the producer may refill it
+      if (r + stages < count) issue(r + stages, r >> 5);
+      z2 = warp_sum(z2);
+      if (b < K && b != a && !(gap > refine_threshold(z2, e2max))) {     // warp-uniform: inside the tf32 error bound
+        const float4* br = reinterpret_cast<const float4*>(E + b * (int64_t)D);
+        float4 bv[VPL];
+        double da = 0.0, db = 0.0;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int col = lane + v * 32;
+          bv[v] = (col < nvec) ? __ldg(br + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          if (lane + v * 32 < nvec) { da += sqdiff4(zv[v], ev[v]); db += sqdiff4(zv[v], bv[v]); }
+        }
+        da = warp_sum(da);
+        db = warp_sum(db);
+        if (db < da || (db == da && b < a)) {        // the runner-up is the exact winner
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) ev[v] = bv[v];
+          if (lane == (r & 31)) { final_code = b; idx[row0 + r] = b; }
+        }
+      }
+      float4* out = reinterpret_cast<float4*>(z_q + (row0 + r) * (int64_t)D);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int col = lane + v * 32;
+        if (col < nvec) {
+          const float4 x = zv[v], e = ev[v];
+          float4 d, o;
+          d.x = e.x - x.x; d.y = e.y - x.y; d.z = e.z - x.z; d.w = e.w - x.w;   // fl(q - z)
+          o.x = x.x + d.x; o.y = x.y + d.y; o.z = x.z + d.z; o.w = x.w + d.w;   // fl(z + fl(q - z))  (:80)
+          acc = fmaf(d.x, d.x, acc); acc = fmaf(d.y, d.y, acc);
+          acc = fmaf(d.z, d.z, acc); acc = fmaf(d.w, d.w, acc);
+          st_stream(out + col, o);
+        }
+      }
+      if ((r & 31) == 31 || r == count - 1) {
+        // end of a chunk of 32 rows: histogram of the final codes (equal codes aggregated), then rotate the chunks
+        const bool mine = ((r & ~31) + lane) < count;
+        const long long code = mine ? (long long)final_code : -1ll;
+        const unsigned peers = __match_any_sync(0xffffffffu, code);
+        if (mine && lane == (__ffs(peers) - 1)) atomicAdd(hist + code, __popc(peers));
+        const int base = ((r >> 5) + 1) * 32;
+        cur_a = nxt_a;
+        final_code = cur_a;
+        nxt_a = load_a(base + 32);
+        cur_w = nxt_w;
+        nxt_w = load_w(base + 32);
+      }
+    }
+  }
+  double wsum = warp_sum((double)acc);
+  if (lane == 0) part[wib] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < QR_WPB; ++i) t += part[i];
+    if (t != 0.0) atomicAdd(sq_sum, t);
+  }
+}
+
+static int launch_quantize_refine(const float* z, const float* E, int64_t* idx, const int64_t* idx2, const float* e2max,
+                                  int64_t N, int D, int64_t K, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st) {
+  const int vpl = (D / 4 + 31) / 32;
+  const size_t sb = (size_t)D * 4 * 2 * QR_WPB;                    // one stage of all 8 warps
+  int stages, bps;
+  const int s2 = (int)((110 * 1024 - QR_BAR_BYTES) / sb);
+  if (s2 >= 4 && vpl <= 4) { stages = s2 > QR_MAX_STAGES ? QR_MAX_STAGES : s2; bps = 2; }
+  else {
+    const int s1 = (int)((220 * 1024 - QR_BAR_BYTES) / sb);
+    stages = s1 > QR_MAX_STAGES ? QR_MAX_STAGES : (s1 < 2 ? 2 : s1);
+    bps = 1;
+  }
+  const size_t smem = QR_BAR_BYTES + (size_t)stages * sb;
+  const int64_t max_warps = (int64_t)sm_count() * bps * QR_WPB;
+  const int64_t chunks = (N + 31) / 32;
+  const int64_t n_warps = chunks < max_warps ? chunks : max_warps;
+  const int rows_per_warp = (int)(((N + n_warps - 1) / n_warps + 31) / 32 * 32);
+  const unsigned blocks = (unsigned)((n_warps + QR_WPB - 1) / QR_WPB);
+  KVQ_REQUIRE((((uintptr_t)z | (uintptr_t)E | (uintptr_t)z_q) & 15) == 0, KVQ_ERR_ARG,
+              "kvq_forward: z, E and z_q must be 16-byte aligned (128-bit / bulk-copy accesses)");
+#define KVQ_QR(V)                                                                                                       \
+  case V:                                                                                                               \
+    KVQ_CUDA(cudaFuncSetAttribute(quantize_refine_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    quantize_refine_kernel<V><<<blocks, QR_WPB * 32, smem, st>>>(z, E, idx, idx2, e2max, N, D, K, z_q, sq_sum, hist,      \
+                                                                 rows_per_warp, stages);                                \
+    break;
+  switch (vpl) {
+    KVQ_QR(1) KVQ_QR(2) KVQ_QR(3) KVQ_QR(4) KVQ_QR(5) KVQ_QR(6) KVQ_QR(7) KVQ_QR(8)
+    default:
+      set_error("kvq_quantize: D=%d not supported (max 1024)", D);
+      return KVQ_ERR_SHAPE;
+  }
+#undef KVQ_QR
+  KVQ_LAUNCH_CHECK();
+  return KVQ_OK;
+}
+
 int launch_quantize(const float* z, const float* E, int64_t* idx, int64_t N, int D, int64_t K,
                     int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st,
                     const ShardPtrs* shards, const int64_t* idx2, const float* e2max) {
   if (N <= 0) return KVQ_OK;
   ShardPtrs sp;
   if (shards) sp = *shards; else { sp.n = 0; sp.k_per = 1; }
-  const bool refine = idx2 != nullptr;
-  KVQ_REQUIRE(!refine || (e2max && sp.n == 0 && k_offset == 0), KVQ_ERR_ARG,
-              "kvq_quantize: the fused top-2 re-evaluation needs an unsharded codebook and the code-norm maximum");
+  if (idx2) {
+    KVQ_REQUIRE(e2max && sp.n == 0 && k_offset == 0, KVQ_ERR_ARG,
+                "kvq_quantize: the fused top-2 re-evaluation needs an unsharded codebook and the code-norm maximum");
+    return launch_quantize_refine(z, E, idx, idx2, e2max, N, D, K, z_q, sq_sum, hist, st);
+  }
   const int wpb = 8;
   const int64_t warps = (N + 31) / 32;
   const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
   const int vpl = (D / 4 + 31) / 32;
-#define KVQ_Q(V)                                                                                                  \
-  case V:                                                                                                         \
-    if (refine)                                                                                                   \
-      quantize_kernel<V, true><<<blocks, wpb * 32, 0, st>>>(z, E, idx, idx2, e2max, N, D, K, k_offset, zero_skipped, \
-                                                            z_q, sq_sum, hist, sp);                               \
-    else                                                                                                          \
-      quantize_kernel<V, false><<<blocks, wpb * 32, 0, st>>>(z, E, idx, nullptr, nullptr, N, D, K, k_offset,        \
-                                                             zero_skipped, z_q, sq_sum, hist, sp);                \
+#define KVQ_Q(V)                                                                                            \
+  case V:                                                                                                   \
+    quantize_kernel<V><<<blocks, wpb * 32, 0, st>>>(z, E, idx, N, D, K, k_offset, zero_skipped, z_q, sq_sum, hist, sp); \
     break;
   switch (vpl) {
     KVQ_Q(1) KVQ_Q(2) KVQ_Q(3) KVQ_Q(4) KVQ_Q(5) KVQ_Q(6) KVQ_Q(7) KVQ_Q(8)

@@ -103,6 +103,47 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- per-warp shared-memory row rings fed by cp.async.bulk (the HBM-bound kernels) -----------------------------
+// A lane-elected producer copies whole rows (global -> shared) with the bulk-copy engine, completion counted on an
+// mbarrier per stage; the warp consumes a stage once its barrier phase flips.  No registers are tied up by bytes in
+// flight, so the ring depth -- not the register file -- sets the memory-level parallelism.
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t ring_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ring_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool ring_mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Spin with a watchdog: a protocol bug traps (the launch reports an error) instead of hanging the GPU.
+__device__ __forceinline__ void ring_mbar_wait(uint32_t bar, uint32_t parity) {
+  if (ring_mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!ring_mbar_try(bar, parity)) {
+    if (((++spins) & 0xfffu) == 0 && clock64() - t0 > 4000000000ll) {  // ~2 s
+      printf("kvq row ring: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+// one row (bytes % 16 == 0, 16-byte aligned on both sides) global -> shared, completion counted on `bar`
+__device__ __forceinline__ void bulk_row_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+#endif  // __CUDACC__
+
 // ---- multi-GPU peer tables (NVLink peer pointers, passed to kernels by value) --------------------------------
 constexpr int MAX_PEERS = 8;
 struct PeerKeys {            // packed-key buffers of every rank of the codebook-sharded group (incl. this rank)

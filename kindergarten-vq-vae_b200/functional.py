@@ -138,6 +138,27 @@ def vq_forward(z: torch.Tensor, E: torch.Tensor, beta: float, *, mode: str = "au
     return scal[0], z_q, scal[1], idx, hist
 
 
+def vq_forward_partials(z: torch.Tensor, E: torch.Tensor, *, mode: str = "auto", ws: Optional[torch.Tensor] = None):
+    """Forward without the finalisation (batch-sharded layer): returns z_q, idx (N,), sq_sum (1 float64), hist (K int32);
+    the caller all-reduces the last two over the ranks and calls `finalize` with the global latent count."""
+    _req(z, "z", torch.float32); _req(E, "E", torch.float32)
+    N, D = z.shape
+    K = E.shape[0]
+    if E.shape[1] != D:
+        raise RuntimeError(f"z has {D} features but the codebook has {E.shape[1]}")
+    z_q = torch.empty_like(z)
+    idx = torch.empty(N, dtype=torch.int64, device=z.device)
+    sq_sum = torch.empty(1, dtype=torch.float64, device=z.device)
+    hist = torch.empty(K, dtype=torch.int32, device=z.device)
+    if ws is None:
+        ws = workspace(N, D, K, z.device)
+    with torch.cuda.device(z.device):
+        check(_lib.load().kvq_forward_partials(z.data_ptr(), E.data_ptr(), N, D, K, SEARCH_MODES[mode], z_q.data_ptr(),
+                                               idx.data_ptr(), sq_sum.data_ptr(), hist.data_ptr(), ws.data_ptr(),
+                                               ws.numel(), _stream()), "kvq_forward_partials")
+    return z_q, idx, sq_sum, hist
+
+
 def vq_backward(z: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, hist: Optional[torch.Tensor], beta: float, *,
                 g_zq: Optional[torch.Tensor] = None, g_loss: Optional[torch.Tensor] = None, need_dz: bool = True,
                 need_dE: bool = True, k_offset: int = 0, n_global: Optional[int] = None,

@@ -16,8 +16,7 @@ exactly two natural ways, and each needs only reductions:
   histogram shards are all-gathered for the perplexity.  The codebook gradient needs no communication at all:
   every rank bucket-sums only the latents that chose one of its codes.
 
-The local compute steps come from a `backend` object (default: the CUDA functional module).  Tests inject a
-CPU stand-in there to exercise this orchestration under gloo without a GPU; the product never does.
+Every local compute step goes through the module-level name `F` (the CUDA functional module, i.e. the C ABI).
 """
 from __future__ import annotations
 
@@ -28,7 +27,7 @@ import torch.distributed as dist
 import torch.nn as nn
 from torch import Tensor
 
-from . import functional as _cuda_backend
+from . import functional as F
 from .vector_quantizer import ONEHOT_AUTO_BYTES
 
 
@@ -38,6 +37,22 @@ def _world(group) -> int:
 
 def _rank(group) -> int:
     return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
+def z_is_cuda(device) -> bool:
+    return torch.device(device).type == "cuda"
+
+
+def _all_reduce_together(tensors, group, device) -> None:
+    """SUM-all-reduce several small tensors of different dtypes as ONE NCCL group launch."""
+    cm = getattr(dist, "_coalescing_manager", None)
+    if cm is not None and torch.device(device).type == "cuda":
+        with cm(group=group, device=torch.device(device), async_ops=False):
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
 def shard_bounds(total: int, parts: int, part: int):
@@ -63,19 +78,19 @@ class _GradPeerMemory:
 
 class _BatchShardedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, E, beta, mode, group, n_global, backend, grad_peer=None):
+    def forward(ctx, z, E, beta, mode, group, n_global, grad_peer=None):
         N, D = z.shape
-        idx, _ = backend.search(z, E, mode=mode)
-        z_q, sq_sum, hist_local = backend.quantize(z, E, idx)
+        # local forward of the layer with the default search machinery (incl. the fused exact top-2 re-evaluation);
+        # its loss / perplexity are per-rank values and are recomputed below from the all-reduced partials
+        z_q, idx, sq_sum, hist_local = F.vq_forward_partials(z, E, mode=mode)
         hist = hist_local.clone()
         if _world(group) > 1:
-            # two small reductions (8 B and 4K B); both are needed before the loss / perplexity exist
-            dist.all_reduce(sq_sum, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
-        loss, perplexity = backend.finalize(sq_sum, hist, n_global, D, beta)
+            # the two partials the loss / perplexity need (8 B and 4K B): ONE coalesced NCCL launch
+            _all_reduce_together([sq_sum, hist], group, z.device)
+        loss, perplexity = F.finalize(sq_sum, hist, n_global, D, beta)
         loss, perplexity = loss.clone(), perplexity.clone()
         ctx.save_for_backward(z, E, idx, hist_local)
-        ctx.beta, ctx.group, ctx.n_global, ctx.backend, ctx.grad_peer = beta, group, n_global, backend, grad_peer
+        ctx.beta, ctx.group, ctx.n_global, ctx.grad_peer = beta, group, n_global, grad_peer
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(perplexity, idx, hist)
         return loss, z_q, perplexity, idx, hist
@@ -93,21 +108,21 @@ class _BatchShardedFn(torch.autograd.Function):
                   else g_loss.detach().to(torch.float32).contiguous())
             gp.buf.zero_()
             gp.handle.barrier(channel=0)                  # every replica is zero before any remote reduction lands
-            dz = _cuda_backend.vq_backward_peers(z, E, idx, hist_local, ctx.beta, g_zq=g_zq, g_loss=gl, need_dz=need_dz,
+            dz = F.vq_backward_peers(z, E, idx, hist_local, ctx.beta, g_zq=g_zq, g_loss=gl, need_dz=need_dz,
                                                  n_global=ctx.n_global, dE_peer_ptrs=gp.handle.buffer_ptrs,
                                                  dE_multicast_ptr=gp.multicast_ptr, my_rank=_rank(ctx.group))
             gp.handle.barrier(channel=1)                  # all ranks' reductions are complete
-            return dz, gp.buf.clone(), None, None, None, None, None, None
+            return dz, gp.buf.clone(), None, None, None, None, None
         if g_loss is None:
             dz = g_zq if need_dz else None
             dE = torch.zeros_like(E) if need_dE else None
         else:
             g_loss = g_loss.detach().to(torch.float32).contiguous()
-            dz, dE = ctx.backend.vq_backward(z, E, idx, hist_local, ctx.beta, g_zq=g_zq, g_loss=g_loss,
-                                             need_dz=need_dz, need_dE=need_dE, n_global=ctx.n_global)
+            dz, dE = F.vq_backward(z, E, idx, hist_local, ctx.beta, g_zq=g_zq, g_loss=g_loss,
+                                   need_dz=need_dz, need_dE=need_dE, n_global=ctx.n_global)
         if need_dE and _world(ctx.group) > 1:
             dist.all_reduce(dE, op=dist.ReduceOp.SUM, group=ctx.group)   # codebook gradient of the global batch
-        return dz, dE, None, None, None, None, None, None
+        return dz, dE, None, None, None, None, None
 
 
 class BatchShardedVectorQuantizer(nn.Module):
@@ -116,8 +131,9 @@ class BatchShardedVectorQuantizer(nn.Module):
     gradient is all-reduced here -- do not also wrap `embedding.weight` in DistributedDataParallel."""
 
     def __init__(self, n_e, e_dim, beta, vq_codebook_init_values: Tensor = None, *, process_group=None,
-                 search: str = "auto", min_encodings=False, backend=None, exchange: str = "nccl"):
-        """exchange="nccl": all-reduce(SUM) of dE after the backward kernel.  exchange="nvlink": the all-reduce is fused
+                 search: str = "auto", min_encodings=False, exchange: str = "nccl"):
+        """exchange="nccl" (default; the all-reduce keeps dE bitwise reproducible): all-reduce(SUM) of dE after the backward
+        kernel.  exchange="nvlink": the all-reduce is fused
         into the scatter-add kernel (multimem.red through the NVSwitch when the symmetric buffer has a multicast
         address, else one system-scope red per peer); needs torch symmetric memory, world <= 8."""
         super().__init__()
@@ -128,7 +144,6 @@ class BatchShardedVectorQuantizer(nn.Module):
         self.exchange = exchange
         self._grad_peer = None
         self.return_min_encodings = min_encodings
-        self.backend = backend if backend is not None else _cuda_backend
         self.embedding = nn.Embedding(n_e, e_dim)
         if vq_codebook_init_values is not None:
             self.embedding.weight.data.copy_(vq_codebook_init_values)
@@ -144,12 +159,11 @@ class BatchShardedVectorQuantizer(nn.Module):
         if self.exchange == "nvlink" and _world(self.group) > 1 and self._grad_peer is None:
             self._grad_peer = _GradPeerMemory(self.group, self.n_e, self.e_dim, z.device)
         loss, z_q, perplexity, idx, _ = _BatchShardedFn.apply(zf, self.embedding.weight, float(self.beta),
-                                                               self.search, self.group, int(n_global), self.backend,
-                                                               self._grad_peer)
+                                                               self.search, self.group, int(n_global), self._grad_peer)
         want = self.return_min_encodings
         if want == "auto":
             want = zf.shape[0] * self.n_e * 4 <= ONEHOT_AUTO_BYTES
-        onehot = self.backend.onehot(idx, self.n_e) if want else None
+        onehot = F.onehot(idx, self.n_e) if want else None
         return loss, z_q.view(z.shape), perplexity, onehot, idx.reshape((batch_size, seq_len, 1))
 
 
@@ -158,16 +172,16 @@ class BatchShardedVectorQuantizer(nn.Module):
 # ------------------------------------------------------------------------------------------------
 class _CodebookShardedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, E_param, beta, mode, group, k_offset, k_total, backend):
+    def forward(ctx, z, E_param, beta, mode, group, k_offset, k_total):
         N, D = z.shape
         world = _world(group)
         k_valid = max(0, min(E_param.shape[0], k_total - k_offset))     # rows past the end of the codebook are padding
         E_local = E_param[:k_valid]
-        _, keys = backend.search(z, E_local, mode=mode, k_offset=k_offset, want_idx=False, want_keys=True)
+        _, keys = F.search(z, E_local, mode=mode, k_offset=k_offset, want_idx=False, want_keys=True)
         if world > 1:
             dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)      # cross-GPU (distance, index) argmin
-        idx = backend.keys_to_idx(keys)
-        z_q, sq_sum, hist_local = backend.quantize(z, E_local, idx, k_offset=k_offset, zero_skipped=True)
+        idx = F.keys_to_idx(keys)
+        z_q, sq_sum, hist_local = F.quantize(z, E_local, idx, k_offset=k_offset, zero_skipped=True)
         if world > 1:
             dist.all_reduce(z_q, op=dist.ReduceOp.SUM, group=group)       # each row is non-zero on exactly one rank
             dist.all_reduce(sq_sum, op=dist.ReduceOp.SUM, group=group)
@@ -179,10 +193,10 @@ class _CodebookShardedFn(torch.autograd.Function):
             hist = torch.cat(parts)[:k_total].contiguous()
         else:
             hist = hist_local
-        loss, perplexity = backend.finalize(sq_sum, hist, N, D, beta)
+        loss, perplexity = F.finalize(sq_sum, hist, N, D, beta)
         loss, perplexity = loss.clone(), perplexity.clone()
         ctx.save_for_backward(z, E_param, idx, hist_local, z_q)
-        ctx.beta, ctx.k_offset, ctx.backend, ctx.k_valid = beta, k_offset, backend, k_valid
+        ctx.beta, ctx.k_offset, ctx.k_valid = beta, k_offset, k_valid
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(perplexity, idx, hist)
         return loss, z_q, perplexity, idx, hist
@@ -195,18 +209,18 @@ class _CodebookShardedFn(torch.autograd.Function):
             g_zq = g_zq.contiguous()
         if g_loss is None:
             return (g_zq if need_dz else None), (torch.zeros_like(E_param) if need_dE else None), None, None, None, \
-                None, None, None
+                None, None
         g_loss = g_loss.detach().to(torch.float32).contiguous()
-        dz = ctx.backend.dz_from_zq(z, z_q, g_zq, g_loss, z.shape[0]) if need_dz else None
+        dz = F.dz_from_zq(z, z_q, g_zq, g_loss, z.shape[0]) if need_dz else None
         dE = None
         if need_dE:   # local: only latents that chose one of this rank's codes contribute
-            dE = _local_codebook_grad(ctx.backend, z, E_param, ctx.k_valid, idx, hist_local, ctx.beta, g_loss, ctx.k_offset)
-        return dz, dE, None, None, None, None, None, None
+            dE = _local_codebook_grad(z, E_param, ctx.k_valid, idx, hist_local, ctx.beta, g_loss, ctx.k_offset)
+        return dz, dE, None, None, None, None, None
 
 
-def _local_codebook_grad(backend, z, E_param, k_valid, idx, hist_local, beta, g_loss, k_offset):
+def _local_codebook_grad(z, E_param, k_valid, idx, hist_local, beta, g_loss, k_offset):
     """dE of this rank's shard (padding rows, if any, get exact zeros)."""
-    _, dE = backend.vq_backward(z, E_param[:k_valid], idx, hist_local, beta, g_zq=None, g_loss=g_loss, need_dz=False,
+    _, dE = F.vq_backward(z, E_param[:k_valid], idx, hist_local, beta, g_zq=None, g_loss=g_loss, need_dz=False,
                                 need_dE=True, k_offset=k_offset)
     if k_valid == E_param.shape[0]:
         return dE
@@ -251,13 +265,13 @@ class _CodebookShardedFusedFn(torch.autograd.Function):
         keys.fill_(torch.iinfo(torch.int64).max)
         peer.mirror.copy_(E_param.detach())
         kh.barrier(channel=0)                       # every rank's key buffer is initialised, every mirror refreshed
-        _cuda_backend.search_peers(z, E_local, kh.buffer_ptrs, rank, mode=mode, k_offset=k_offset)
+        F.search_peers(z, E_local, kh.buffer_ptrs, rank, mode=mode, k_offset=k_offset)
         kh.barrier(channel=1)                       # all remote atomics have landed: keys hold the global argmin
-        idx = _cuda_backend.keys_to_idx(keys)
-        z_q, sq_sum, hist_all = _cuda_backend.quantize_shards(z, peer.mirror_h.buffer_ptrs, k_per, idx, k_per * world)
+        idx = F.keys_to_idx(keys)
+        z_q, sq_sum, hist_all = F.quantize_shards(z, peer.mirror_h.buffer_ptrs, k_per, idx, k_per * world)
         kh.barrier(channel=0)                       # peers are done reading this rank's mirror
         hist = hist_all[:k_total].contiguous()
-        loss, perplexity = _cuda_backend.finalize(sq_sum, hist, N, D, beta)
+        loss, perplexity = F.finalize(sq_sum, hist, N, D, beta)
         loss, perplexity = loss.clone(), perplexity.clone()
         hist_local = hist_all[k_offset:k_offset + k_valid].contiguous()
         ctx.save_for_backward(z, E_param, idx, hist_local, z_q)
@@ -276,10 +290,10 @@ class _CodebookShardedFusedFn(torch.autograd.Function):
         if g_loss is None:
             return ((g_zq if need_dz else None), (torch.zeros_like(E_param) if need_dE else None)) + none
         g_loss = g_loss.detach().to(torch.float32).contiguous()
-        dz = _cuda_backend.dz_from_zq(z, z_q, g_zq, g_loss, z.shape[0]) if need_dz else None
+        dz = F.dz_from_zq(z, z_q, g_zq, g_loss, z.shape[0]) if need_dz else None
         dE = None
         if need_dE:
-            dE = _local_codebook_grad(_cuda_backend, z, E_param, ctx.k_valid, idx, hist_local, ctx.beta, g_loss, ctx.k_offset)
+            dE = _local_codebook_grad(z, E_param, ctx.k_valid, idx, hist_local, ctx.beta, g_loss, ctx.k_offset)
         return (dz, dE) + none
 
 
@@ -289,16 +303,17 @@ class CodebookShardedVectorQuantizer(nn.Module):
     codebook (all shards have ceil(n_e / world) rows; the tail of the last one is padding the kernels never see)."""
 
     def __init__(self, n_e, e_dim, beta, vq_codebook_init_values: Tensor = None, *, process_group=None,
-                 search: str = "auto", backend=None, exchange: str = "nccl"):
-        """exchange="nccl": all-reduce(MIN) of keys + all-reduce(SUM) of z_q partials (works everywhere);
-        exchange="nvlink": fused path -- the kernels do the exchange themselves over NVLink peer memory
-        (needs torch symmetric memory on one NVLink domain, world <= 8)."""
+                 search: str = "auto", exchange: str = "auto"):
+        """exchange="nvlink": fused path -- the kernels do the exchange themselves over NVLink peer memory (system-scope
+        atomics for the argmin, peer loads for the winning rows; needs torch symmetric memory on one NVLink domain,
+        world <= 8).  exchange="nccl": all-reduce(MIN) of keys + all-reduce(SUM) of the N x D z_q partials (works
+        everywhere, moves 2 x N x D x 4 bytes more).  exchange="auto" (default): "nvlink" when the symmetric-memory
+        rendezvous succeeds on every rank, else "nccl"."""
         super().__init__()
         self.n_e, self.e_dim, self.beta = n_e, e_dim, beta
         self.search, self.group = search, process_group
-        self.backend = backend if backend is not None else _cuda_backend
-        if exchange not in ("nccl", "nvlink"):
-            raise ValueError("exchange must be 'nccl' or 'nvlink'")
+        if exchange not in ("auto", "nccl", "nvlink"):
+            raise ValueError("exchange must be 'auto', 'nccl' or 'nvlink'")
         self.exchange = exchange
         self._peer = None
         world, rank = _world(process_group), _rank(process_group)
@@ -323,6 +338,8 @@ class CodebookShardedVectorQuantizer(nn.Module):
     def forward(self, z: Tensor, device=None):
         batch_size, seq_len, _ = z.shape
         zf = z.view((-1, self.e_dim))
+        if self.exchange == "auto" and self.world > 1:
+            self.exchange = self._resolve_exchange(z.device)
         if self.exchange == "nvlink" and self.world > 1:
             if self._peer is None:
                 self._peer = _PeerMemory(self.group, self.k_per, self.e_dim, z.device)
@@ -331,6 +348,23 @@ class CodebookShardedVectorQuantizer(nn.Module):
                 self.k_offset, self.n_e)
             return loss, z_q.view(z.shape), perplexity, None, idx.reshape((batch_size, seq_len, 1))
         loss, z_q, perplexity, idx, _ = _CodebookShardedFn.apply(zf, self.embedding.weight, float(self.beta),
-                                                                  self.search, self.group, self.k_offset, self.n_e,
-                                                                  self.backend)
+                                                                  self.search, self.group, self.k_offset, self.n_e)
         return loss, z_q.view(z.shape), perplexity, None, idx.reshape((batch_size, seq_len, 1))
+
+    def _resolve_exchange(self, device) -> str:
+        """"nvlink" iff every rank can set up the peer-mapped buffers (torch symmetric memory: CUDA VMM + fabric / IPC
+        handles); decided once, collectively, so that all ranks take the same path."""
+        ok = 1
+        try:
+            if not z_is_cuda(device) or self.world > 8:
+                raise RuntimeError("fused exchange needs CUDA and world <= 8")
+            self._peer = _PeerMemory(self.group, self.k_per, self.e_dim, device)
+        except Exception:
+            self._peer = None
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            return "nvlink"
+        self._peer = None
+        return "nccl"

@@ -10,7 +10,7 @@ Shelgon.py:58) is materialised only when it is small or explicitly requested, ot
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -22,42 +22,77 @@ from . import functional as F
 ONEHOT_AUTO_BYTES = 64 << 20
 
 
-class _VQFunction(torch.autograd.Function):
-    """forward(z_flat, E) -> (loss, z_q, perplexity, idx, hist); backward per SURVEY.md section 3.3."""
+# ---- the layer as two dispatcher-registered operators -------------------------------------------------------------
+# `torch.library.custom_op` (with fake / meta implementations and a registered autograd formula) instead of a bare
+# autograd.Function: the reference wraps the whole model in `model.compile()` (models/shelgon3/main.py:83), and an
+# opaque custom op is traced as ONE graph node -- no graph break around the layer, `fullgraph=True` works.
+# Each op is a thin call into the C ABI; nothing here computes.
 
-    @staticmethod
-    def forward(ctx, z: Tensor, E: Tensor, beta: float, mode: str, ws: Optional[Tensor]):
-        loss, z_q, perplexity, idx, hist = F.vq_forward(z, E, beta, mode=mode, ws=ws)
-        # fresh 0-d tensors (not views of the 2-float result buffer): the training loop multiplies the loss in
-        # place (models/shelgon3/Trainer.py:104)
-        loss, perplexity = loss.clone(), perplexity.clone()
-        ctx.save_for_backward(z, E, idx, hist)
-        ctx.beta = beta
-        ctx.ws = ws
-        ctx.set_materialize_grads(False)
-        ctx.mark_non_differentiable(perplexity, idx, hist)
-        return loss, z_q, perplexity, idx, hist
+@torch.library.custom_op("kvq::vq_forward", mutates_args=())
+def _vq_forward_op(z: Tensor, E: Tensor, beta: float, mode: str) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    loss, z_q, perplexity, idx, hist = F.vq_forward(z, E, beta, mode=mode)
+    # fresh 0-d tensors (not views of the 2-float result buffer): the training loop multiplies the loss in place
+    # (models/shelgon3/Trainer.py:104)
+    return loss.clone(), z_q, perplexity.clone(), idx, hist
 
-    @staticmethod
-    def backward(ctx, g_loss, g_zq, g_perp, g_idx, g_hist):
-        z, E, idx, hist = ctx.saved_tensors
-        need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if g_loss is None and g_zq is None:
-            return None, None, None, None, None
-        if g_zq is not None:
-            g_zq = g_zq.contiguous()
-            if g_zq.dtype != torch.float32:
-                g_zq = g_zq.float()
-        if g_loss is not None:
-            g_loss = g_loss.detach().to(torch.float32).contiguous()
-        if g_loss is None:
-            # loss unused: dz = g_zq exactly, dE = 0
-            dz = g_zq if need_dz else None
-            dE = torch.zeros_like(E) if need_dE else None
-            return dz, dE, None, None, None
-        dz, dE = F.vq_backward(z, E, idx, hist, ctx.beta, g_zq=g_zq, g_loss=g_loss, need_dz=need_dz,
-                               need_dE=need_dE, ws=ctx.ws)
-        return dz, dE, None, None, None
+
+@_vq_forward_op.register_fake
+def _(z, E, beta, mode):
+    N, K = z.shape[0], E.shape[0]
+    return (z.new_empty(()), torch.empty_like(z), z.new_empty(()), z.new_empty((N,), dtype=torch.int64),
+            z.new_empty((K,), dtype=torch.int32))
+
+
+@torch.library.custom_op("kvq::vq_backward", mutates_args=())
+def _vq_backward_op(z: Tensor, E: Tensor, idx: Tensor, hist: Tensor, g_zq: Optional[Tensor], g_loss: Tensor, beta: float,
+                    need_dz: bool, need_dE: bool) -> Tuple[Tensor, Tensor]:
+    if g_zq is not None:
+        g_zq = g_zq.contiguous()
+        if g_zq.dtype != torch.float32:
+            g_zq = g_zq.float()
+    g_loss = g_loss.detach().to(torch.float32).contiguous()
+    dz, dE = F.vq_backward(z, E, idx, hist, beta, g_zq=g_zq, g_loss=g_loss, need_dz=need_dz, need_dE=need_dE)
+    # an operator cannot return None: an unrequested gradient comes back as an empty tensor
+    return (dz if dz is not None else z.new_empty(0)), (dE if dE is not None else E.new_empty(0))
+
+
+@_vq_backward_op.register_fake
+def _(z, E, idx, hist, g_zq, g_loss, beta, need_dz, need_dE):
+    return (torch.empty_like(z) if need_dz else z.new_empty(0)), (torch.empty_like(E) if need_dE else E.new_empty(0))
+
+
+@torch.library.custom_op("kvq::onehot", mutates_args=())
+def _onehot_op(idx: Tensor, n_e: int) -> Tensor:
+    return F.onehot(idx, n_e)
+
+
+@_onehot_op.register_fake
+def _(idx, n_e):
+    return idx.new_empty((idx.numel(), n_e), dtype=torch.float32)
+
+
+def _vq_setup_context(ctx, inputs, output):
+    z, E, beta, _mode = inputs
+    _loss, _z_q, _perp, idx, hist = output
+    ctx.save_for_backward(z, E, idx, hist)
+    ctx.beta = beta
+    ctx.set_materialize_grads(False)
+
+
+def _vq_backward(ctx, g_loss, g_zq, g_perp, g_idx, g_hist):
+    """dz = g_zq + g_loss 2 (z - q)/(N D);  dE[k] = g_loss beta 2/(N D) sum_{i in k} (q_i - z_i)."""
+    z, E, idx, hist = ctx.saved_tensors
+    need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    if g_loss is None and g_zq is None:
+        return None, None, None, None
+    if g_loss is None:
+        # loss unused: dz = g_zq exactly, dE = 0
+        return (g_zq if need_dz else None), (torch.zeros_like(E) if need_dE else None), None, None
+    dz, dE = _vq_backward_op(z, E, idx, hist, g_zq, g_loss, ctx.beta, need_dz, need_dE)
+    return (dz if need_dz else None), (dE if need_dE else None), None, None
+
+
+_vq_forward_op.register_autograd(_vq_backward, setup_context=_vq_setup_context)
 
 
 class VectorQuantizer(nn.Module):
@@ -93,15 +128,7 @@ class VectorQuantizer(nn.Module):
             self.embedding.weight.data.copy_(vq_codebook_init_values)
         else:
             self.embedding.weight.data.uniform_(-1.0 / self.n_e, 1.0 / self.n_e)
-        self._ws = None
 
-    def _workspace(self, N: int, device) -> Tensor:
-        need = F._lib.load().kvq_workspace_bytes(N, self.e_dim, self.n_e)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._ws
-
-    @torch.compiler.disable
     def forward(self, z: torch.Tensor, device=None):
         """
         z (continuous) -> z_q (discrete);  z.shape = (batch, seq_len, channel), channel == e_dim.
@@ -120,14 +147,13 @@ class VectorQuantizer(nn.Module):
             raise RuntimeError("VectorQuantizer (kvq) runs on CUDA only: there is no CPU fallback "
                                f"(z on {z.device}, codebook on {weight.device})")
         N = z_flattened.shape[0]
-        ws = self._workspace(N, z.device)
-        loss, z_q, perplexity, idx, _hist = _VQFunction.apply(z_flattened, weight, float(self.beta), self.search, ws)
+        loss, z_q, perplexity, idx, _hist = _vq_forward_op(z_flattened, weight, float(self.beta), self.search)
         z_q = z_q.view(z.shape)
 
         want = self.return_min_encodings
         if want == "auto":
             want = N * self.n_e * 4 <= ONEHOT_AUTO_BYTES
-        min_encodings = F.onehot(idx, self.n_e) if want else None    # VectorQuantizer.py:67-68
+        min_encodings = _onehot_op(idx, self.n_e) if want else None    # VectorQuantizer.py:67-68
 
         min_encoding_indices = idx.reshape((batch_size, seq_len, 1))  # VectorQuantizer.py:90
         return loss, z_q, perplexity, min_encodings, min_encoding_indices

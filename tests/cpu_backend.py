@@ -1,5 +1,6 @@
-"""CPU stand-in for the CUDA functional backend, built on the oracle.  TEST INFRASTRUCTURE: injected into the
-sharded modules so that their collective orchestration can be exercised under gloo without a GPU."""
+"""CPU stand-in for the CUDA functional module, built on the oracle.  TEST INFRASTRUCTURE: tests/test_sharded_gloo.py
+monkeypatches it over `sharded.F` so that the collective orchestration of the sharded layers can be exercised under gloo
+without a GPU.  The product has no such seam."""
 import ctypes
 
 import numpy as np
@@ -20,13 +21,19 @@ def _pack(scores: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
 
 def search(z, E, *, mode="auto", k_offset=0, want_idx=True, want_keys=False, keys=None, keys_accumulate=False, ws=None):
     s = torch.sum(E ** 2, dim=1) - 2 * torch.matmul(z, E.t())
-    s = torch.where(torch.isnan(s), torch.full_like(s, float("inf")), s)
-    v, i = torch.min(s, dim=1)
+    i = torch.argmin(s, dim=1)                       # NaN counts as the minimum, like the kernels
+    v = s.gather(1, i[:, None]).squeeze(1)
     idx = (i + k_offset) if want_idx else None
     k = _pack(v, i + k_offset) if (want_keys or keys is not None) else None
     if keys is not None:
         k = torch.minimum(k, keys)
     return idx, k
+
+
+def vq_forward_partials(z, E, *, mode="auto", ws=None):
+    idx, _ = search(z, E, mode=mode)
+    z_q, sq, h = quantize(z, E, idx)
+    return z_q, idx, sq, h
 
 
 def keys_to_idx(keys):

@@ -38,12 +38,16 @@ class Shelgon(torch.nn.Module):
         return vq_loss, perplexity, idx, logits
 
 
-def train_step(model, opt, input_ids, mask, dev, vq_weight=1.0):
-    """Trainer.py:87-115."""
+def train_step(model, opt, input_ids, mask, dev, vq_weight=1.0, fused_recon=False):
+    """Trainer.py:87-115.  fused_recon: kvq.recon_loss (one pass over the logits) instead of the reference expressions."""
     loss_vq, perp, idx, logits = model.forward(input_ids, mask, dev, True)
-    target = Fn.one_hot(input_ids, VOCAB).float()
-    loss_recon = Fn.kl_div(Fn.log_softmax(logits, dim=-1), target, reduction="batchmean")           # :94-98
-    recon_ids = torch.argmax(torch.softmax(logits, dim=-1), dim=-1)                                  # :100
+    if fused_recon:
+        from kindergarten_vq_vae_b200 import recon_loss
+        loss_recon, recon_ids, _acc, _per = recon_loss(logits, input_ids)
+    else:
+        target = Fn.one_hot(input_ids, VOCAB).reshape(-1, VOCAB).float()
+        loss_recon = Fn.kl_div(Fn.log_softmax(logits.reshape(-1, VOCAB), dim=-1), target, reduction="batchmean")  # :94-98
+        recon_ids = torch.argmax(torch.softmax(logits, dim=-1), dim=-1)                              # :100
     loss_vq *= vq_weight                                                                             # :104 (in place)
     loss_full = loss_recon + loss_vq
     opt.zero_grad()
@@ -82,7 +86,7 @@ def main():
             model, opt = build(kind, dev, 123)
             losses = []
             for i in range(8):
-                out = train_step(model, opt, batches[i % 4], mask, dev)
+                out = train_step(model, opt, batches[i % 4], mask, dev, fused_recon=(kind == "kvq"))
                 losses.append((float(out[0]), float(out[1]), float(out[2])))
                 if i == 0:
                     first_idx = out[3].clone()
@@ -90,7 +94,7 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(10):
-                out = train_step(model, opt, batches[i % 4], mask, dev)
+                out = train_step(model, opt, batches[i % 4], mask, dev, fused_recon=(kind == "kvq"))
             e1.record(); torch.cuda.synchronize()
             ms_step = e0.elapsed_time(e1) / 10
             # the VQ layer alone inside this model: forward + backward on the encoder's latents

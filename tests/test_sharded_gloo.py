@@ -23,13 +23,15 @@ def _worker(rank, world, port, mode, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     import cpu_backend
+    import kindergarten_vq_vae_b200 as kvq
     from kindergarten_vq_vae_b200 import BatchShardedVectorQuantizer, CodebookShardedVectorQuantizer
+    kvq.sharded.F = cpu_backend          # the test seam: the sharded layers call everything through `sharded.F`
     g = load_golden("wide")
     z, E, gz, beta, w = g["z"], g["E"], g["gz"], float(g["beta"]), float(g["w"])
     B = z.shape[0]
     try:
         if mode == "batch":
-            vq = BatchShardedVectorQuantizer(E.shape[0], E.shape[1], beta, E, backend=cpu_backend)
+            vq = BatchShardedVectorQuantizer(E.shape[0], E.shape[1], beta, E)
             lo, hi = rank * B // world, (rank + 1) * B // world
             zl = z[lo:hi].clone().requires_grad_(True)
             loss, z_q, perp, _, idx = vq.forward(zl, "cpu")
@@ -39,7 +41,9 @@ def _worker(rank, world, port, mode, q):
         else:
             if mode == "codebook_uneven":
                 E = E[:511].contiguous()            # 511 codes over 2 ranks: shards of 256 and 255 (+1 padding row)
-            vq = CodebookShardedVectorQuantizer(E.shape[0], E.shape[1], beta, E, backend=cpu_backend)
+            # "auto" must settle on the NCCL-style collectives when peer memory is not available (CPU / gloo here)
+            vq = CodebookShardedVectorQuantizer(E.shape[0], E.shape[1], beta, E,
+                                                exchange="nccl" if mode == "codebook" else "auto")
             zl = z.clone().requires_grad_(True)
             loss, z_q, perp, _, idx = vq.forward(zl, "cpu")
             (loss * w + (z_q * gz).sum()).backward()
