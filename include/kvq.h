@@ -212,6 +212,34 @@ int kvq_recon_loss_forward(const float* logits, const int64_t* ids, int64_t B, i
 int kvq_recon_loss_backward(const float* logits, const int64_t* ids, const float* row_lse, const float* g_loss, int64_t B,
                             int64_t S, int64_t V, float* dlogits, kvq_stream_t stream);
 
+/* ---- Gumbel-softmax quantiser: the reference's alternative VQ_MODE (models/shelgon3/GumbelQuantizer.py:43-83) ----
+ * Building blocks; the host-side mirror of the reference class (gumbel.py) strings them together.
+ *
+ * kvq_gemm_nt: C (M x ldc) = alpha * A (M x Kc) B^T (n x Kc) + bias[n] on the tcgen05 tf32 path (fp32 accumulate, TMA-fed,
+ * the search kernel with a store epilogue).  A and B are dense row-major with leading dimension Kc; Kc % 32 == 0,
+ * ldc % 4 == 0, columns [n, ldc) of C are written as zeros.  bias may be NULL.
+ * kvq_transpose_pad: dst (C x ldd) = src^T for src (R x C, leading dimension lds); columns [R, ldd) are zero-filled. */
+int kvq_gemm_nt(const float* A, const float* B, int64_t M, int64_t n, int64_t Kc, float* C, int64_t ldc, const float* bias,
+                float alpha, kvq_stream_t stream);
+int kvq_transpose_pad(const float* src, int64_t R, int64_t C, int64_t lds, float* dst, int64_t ldd, kvq_stream_t stream);
+/* Per-row part of GumbelQuantizer.forward (:57-74) on logits (N x ldk, K valid columns):
+ *   y_soft = softmax((logits + g) / tau); y = one_hot(argmax) - y_soft + y_soft (hard) or y_soft; ind = argmax;
+ *   diff = kld_scale * mean_n sum_k q log(q K + 1e-10), q = softmax(logits).
+ * noise (N x K, the Gumbel sample g) may be NULL: it is then generated from `seed` by a counter-based generator (the
+ * backward regenerates it from the same seed).  y is N x ldk (padding zeroed), kl_row is N floats of scratch. */
+int kvq_gumbel_rows_forward(const float* logits, const float* noise, uint64_t seed, int64_t N, int64_t K, int64_t ldk,
+                            float tau, float kld_scale, int hard, float* y, int64_t* ind, float* diff, float* kl_row,
+                            kvq_stream_t stream);
+/* hard mode: z_q[n] = y[n, ind[n]] * E[ind[n]] (the einsum of :64 when every other weight is an exact zero). */
+int kvq_gumbel_hard_gather(const float* y, const int64_t* ind, const float* E, int64_t N, int D, int64_t ldk, float* z_q,
+                           kvq_stream_t stream);
+/* dL = d(total)/d(logits) from dy = d(total)/dy (N x ldk, may be NULL) and the DEVICE scalar g_diff = d(total)/d(diff)
+ * (may be NULL): softmax backward of both softmaxes, straight-through for the hard one-hot. */
+int kvq_gumbel_rows_backward(const float* logits, const float* noise, uint64_t seed, const float* dy, const float* g_diff,
+                             int64_t N, int64_t K, int64_t ldk, float tau, float kld_scale, float* dL, kvq_stream_t stream);
+/* out[k] = sum_n a[n, k] for the first K columns of an (N x ld) matrix (the bias gradient), fixed summation order. */
+int kvq_colsum(const float* a, int64_t N, int64_t K, int64_t ld, float* out, kvq_stream_t stream);
+
 /* Token-id corruption helpers.  common/tensor_utils.py:13-49 and :52-87, with a counter-based device RNG
  * (seeded; the reference uses the host RNG, so parity is distributional: exact counts, value ranges).
  *  - replace: exactly floor(numel*pct) positions (a seeded random subset) receive uniform ints in [low, high).

@@ -16,7 +16,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB = os.path.join(PKG_DIR, "libkvq.so")
 STAMP = os.path.join(PKG_DIR, "build", "libkvq.stamp")
-SOURCES = ["api.cu", "bandwidth_kernels.cu", "backward.cu", "search_fp32.cu", "search_tf32.cu", "aux.cu", "recon.cu"]
+SOURCES = ["api.cu", "bandwidth_kernels.cu", "backward.cu", "search_fp32.cu", "search_tf32.cu", "aux.cu", "recon.cu", "gumbel.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false"]
 

@@ -80,7 +80,10 @@ struct HostPipe {
     cap_rows = cap_codes = cap_ws = 0; cap_D = 0; device = -1;
   }
 };
-static HostPipe g_pipe;
+// one staging pipeline per device (its own buffers, streams and lock): host threads driving different GPUs neither
+// serialise on each other nor evict each other's staging buffers
+constexpr int MAX_DEVICES = 64;
+static HostPipe g_pipes[MAX_DEVICES];
 
 static int ensure_pipe(HostPipe& hp, int64_t N, int D, int64_t K) {
   int dev = 0;
@@ -139,8 +142,15 @@ int kvq_change_percentage_of_elements(const int64_t* in, int64_t R, int64_t C, i
 }
 
 int kvq_host_release(void) {
-  std::lock_guard<std::mutex> lock(g_pipe.mu);
-  g_pipe.release();
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (int d = 0; d < MAX_DEVICES; ++d) {
+    std::lock_guard<std::mutex> lock(g_pipes[d].mu);
+    if (g_pipes[d].device < 0) continue;
+    cudaSetDevice(g_pipes[d].device);
+    g_pipes[d].release();
+  }
+  cudaSetDevice(prev);
   return KVQ_OK;
 }
 
@@ -182,8 +192,11 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   const int64_t chunks = (int64_t)bounds.size() - 1;
   KVQ_REQUIRE(chunks <= 4096, KVQ_ERR_ARG, "kvq_forward_backward_host: too many chunks (%lld)", (long long)chunks);
 
-  std::lock_guard<std::mutex> lock(g_pipe.mu);
-  HostPipe& hp = g_pipe;
+  int dev = 0;
+  KVQ_CUDA(cudaGetDevice(&dev));
+  KVQ_REQUIRE(dev >= 0 && dev < MAX_DEVICES, KVQ_ERR_UNSUPPORTED, "kvq_forward_backward_host: device ordinal %d out of range", dev);
+  HostPipe& hp = g_pipes[dev];
+  std::lock_guard<std::mutex> lock(hp.mu);
   rc = ensure_pipe(hp, N, D, K); if (rc) return rc;
   int m = mode;
   if (m == KVQ_SEARCH_AUTO) m = tf32_shape_ok(N, D, K) ? KVQ_SEARCH_TF32_REFINE : KVQ_SEARCH_FP32;

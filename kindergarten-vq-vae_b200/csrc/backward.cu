@@ -374,21 +374,20 @@ __global__ void __launch_bounds__(SEG_WPB * 32, (VPL <= 4) ? 2 : 1) segmented_ke
   int2 nxt = (32 + lane < count) ? slots[p0 + 32 + lane] : make_int2(0, -1);
 
   // producer step: copy the row(s) of slot j into stage j % stages.  Every lane runs the shuffles, lane 0 issues.
-  auto issue = [&](int j, int consumer_chunk) {
+  auto issue = [&](int j, int js, int consumer_chunk) {
     const int src_lane = j & 31;
     const int row_c = __shfl_sync(0xffffffffu, cur.x, src_lane);
     const int row_n = __shfl_sync(0xffffffffu, nxt.x, src_lane);
     if (lane == 0) {
       const int row = ((j >> 5) == consumer_chunk) ? row_c : row_n;
-      const int s = j % stages;
-      const uint32_t bar = bars + 8 * s;
-      const uint32_t dst = ring_u32 + (uint32_t)s * stage_bytes;
+      const uint32_t bar = bars + 8 * js;
+      const uint32_t dst = ring_u32 + (uint32_t)js * stage_bytes;
       ring_mbar_expect_tx(bar, stage_bytes);
       bulk_row_g2s(dst, z + (int64_t)row * D, row_bytes, bar);
       if (has_g) bulk_row_g2s(dst + row_bytes, g_zq + (int64_t)row * D, row_bytes, bar);
     }
   };
-  for (int j = 0; j < stages && j < count; ++j) issue(j, 0);
+  for (int j = 0; j < stages && j < count; ++j) issue(j, j, 0);
 
   float4 acc[VPL], ev[VPL];
 #pragma unroll
@@ -397,9 +396,10 @@ __global__ void __launch_bounds__(SEG_WPB * 32, (VPL <= 4) ? 2 : 1) segmented_ke
     ev[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   int cur_code = -1;
+  int s = 0;                // stage of slot r, and the parity of its barrier phase (no runtime division in the loop)
+  uint32_t phase = 0;
 
   for (int r = 0; r < count; ++r) {
-    const int s = r % stages;
     const int row = __shfl_sync(0xffffffffu, cur.x, r & 31);
     const int code = __shfl_sync(0xffffffffu, cur.y, r & 31);
     if (code != cur_code) {  // warp-uniform: the code is broadcast
@@ -414,9 +414,9 @@ __global__ void __launch_bounds__(SEG_WPB * 32, (VPL <= 4) ? 2 : 1) segmented_ke
         }
       }
     }
-    ring_mbar_wait(bars + 8 * s, (uint32_t)((r / stages) & 1));
-    const float4* zs = reinterpret_cast<const float4*>(ring + (size_t)s * stage_bytes);
-    const float4* gs = reinterpret_cast<const float4*>(ring + (size_t)s * stage_bytes + row_bytes);
+    ring_mbar_wait(bars + 8 * s, phase);
+    const float4* zs = reinterpret_cast<const float4*>(ring + (uint32_t)s * stage_bytes);
+    const float4* gs = reinterpret_cast<const float4*>(ring + (uint32_t)s * stage_bytes + row_bytes);
     float4* out = (!MEAN && dz) ? reinterpret_cast<float4*>(dz + (int64_t)row * D) : nullptr;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(SEG_WPB * 32, (VPL <= 4) ? 2 : 1) segmented_ke
       }
     }
     __syncwarp();                                   // every lane has read stage s: it may be overwritten
-    if (r + stages < count) issue(r + stages, r >> 5);
+    if (r + stages < count) issue(r + stages, s, r >> 5);
+    if (++s == stages) { s = 0; phase ^= 1; }
     if ((r & 31) == 31) {                           // consumer moves to the next chunk; fetch the one after it
       cur = nxt;
       const int base = ((r >> 5) + 2) * 32;

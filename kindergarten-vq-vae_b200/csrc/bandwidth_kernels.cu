@@ -288,42 +288,43 @@ __global__ void __launch_bounds__(QR_WPB * 32, (VPL <= 4) ? 2 : 1) quantize_refi
     const float e2max = *e2max_p;
 
     // lane l holds winner / packed runner-up word of row 32*c + l; one chunk ahead is kept for the producer
-    auto load_a = [&](int base) -> int64_t {
+    auto load_a = [&](int base) -> int {
       int64_t a = 0;
       if (base + lane < count) { a = idx[row0 + base + lane]; if (a < 0 || a >= K) a = 0; }
-      return a;
+      return (int)a;                                   // K < 2^31
     };
     auto load_w = [&](int base) -> unsigned long long {
       return (base + lane < count) ? (unsigned long long)idx2[row0 + base + lane] : 0ull;
     };
-    int64_t cur_a = load_a(0), nxt_a = load_a(32);
+    int cur_a = load_a(0), nxt_a = load_a(32);
     unsigned long long cur_w = load_w(0), nxt_w = load_w(32);
 
-    auto issue = [&](int j, int consumer_chunk) {
-      const long long a_c = __shfl_sync(0xffffffffu, (long long)cur_a, j & 31);
-      const long long a_n = __shfl_sync(0xffffffffu, (long long)nxt_a, j & 31);
+    // producer step: rows of slot j (stage js) -- every lane runs the shuffles, lane 0 issues the two bulk copies
+    auto issue = [&](int j, int js, int consumer_chunk) {
+      const int a_c = __shfl_sync(0xffffffffu, cur_a, j & 31);
+      const int a_n = __shfl_sync(0xffffffffu, nxt_a, j & 31);
       if (lane == 0) {
-        const long long a = ((j >> 5) == consumer_chunk) ? a_c : a_n;
-        const int s = j % stages;
-        const uint32_t bar = bars + 8 * s;
-        const uint32_t dst = ring_u32 + (uint32_t)s * stage_bytes;
+        const int a = ((j >> 5) == consumer_chunk) ? a_c : a_n;
+        const uint32_t bar = bars + 8 * js;
+        const uint32_t dst = ring_u32 + (uint32_t)js * stage_bytes;
         ring_mbar_expect_tx(bar, stage_bytes);
         bulk_row_g2s(dst, z + (row0 + j) * (int64_t)D, row_bytes, bar);
-        bulk_row_g2s(dst + row_bytes, E + a * (int64_t)D, row_bytes, bar);
+        bulk_row_g2s(dst + row_bytes, E + (int64_t)a * D, row_bytes, bar);
       }
     };
-    for (int j = 0; j < stages && j < count; ++j) issue(j, 0);
+    for (int j = 0; j < stages && j < count; ++j) issue(j, j, 0);
 
-    int64_t final_code = cur_a;      // lane l: final code of row 32*chunk + l
+    int final_code = cur_a;          // lane l: final code of row 32*chunk + l
+    int s = 0;                       // stage of row r, and the parity of its barrier phase
+    uint32_t phase = 0;
     for (int r = 0; r < count; ++r) {
-      const int s = r % stages;
-      const int64_t a = __shfl_sync(0xffffffffu, (long long)cur_a, r & 31);
+      const int64_t a = __shfl_sync(0xffffffffu, cur_a, r & 31);
       const unsigned long long w = __shfl_sync(0xffffffffu, cur_w, r & 31);
       int64_t b = (int64_t)(w & 0xffffffffull);
       const float gap = __uint_as_float((unsigned)(w >> 32));
-      ring_mbar_wait(bars + 8 * s, (uint32_t)((r / stages) & 1));
-      const float4* zs = reinterpret_cast<const float4*>(ring + (size_t)s * stage_bytes);
-      const float4* es = reinterpret_cast<const float4*>(ring + (size_t)s * stage_bytes + row_bytes);
+      ring_mbar_wait(bars + 8 * s, phase);
+      const float4* zs = reinterpret_cast<const float4*>(ring + (uint32_t)s * stage_bytes);
+      const float4* es = reinterpret_cast<const float4*>(ring + (uint32_t)s * stage_bytes + row_bytes);
       float4 zv[VPL], ev[VPL];
       float z2 = 0.f;
 #pragma unroll
@@ -340,7 +341,8 @@ __global__ void __launch_bounds__(QR_WPB * 32, (VPL <= 4) ? 2 : 1) quantize_refi
         }
       }
       __syncwarp();                                  // every lane has read stage s: the producer may refill it
-      if (r + stages < count) issue(r + stages, r >> 5);
+      if (r + stages < count) issue(r + stages, s, r >> 5);
+      if (++s == stages) { s = 0; phase ^= 1; }
       z2 = warp_sum(z2);
       if (b < K && b != a && !(gap > refine_threshold(z2, e2max))) {     // warp-uniform: inside the tf32 error bound
         const float4* br = reinterpret_cast<const float4*>(E + b * (int64_t)D);
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(QR_WPB * 32, (VPL <= 4) ? 2 : 1) quantize_refi
         if (db < da || (db == da && b < a)) {        // the runner-up is the exact winner
 #pragma unroll
           for (int v = 0; v < VPL; ++v) ev[v] = bv[v];
-          if (lane == (r & 31)) { final_code = b; idx[row0 + r] = b; }
+          if (lane == (r & 31)) { final_code = (int)b; idx[row0 + r] = b; }
         }
       }
       float4* out = reinterpret_cast<float4*>(z_q + (row0 + r) * (int64_t)D);
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(QR_WPB * 32, (VPL <= 4) ? 2 : 1) quantize_refi
       if ((r & 31) == 31 || r == count - 1) {
         // end of a chunk of 32 rows: histogram of the final codes (equal codes aggregated), then rotate the chunks
         const bool mine = ((r & ~31) + lane) < count;
-        const long long code = mine ? (long long)final_code : -1ll;
+        const int code = mine ? final_code : -1;
         const unsigned peers = __match_any_sync(0xffffffffu, code);
         if (mine && lane == (__ffs(peers) - 1)) atomicAdd(hist + code, __popc(peers));
         const int base = ((r >> 5) + 1) * 32;

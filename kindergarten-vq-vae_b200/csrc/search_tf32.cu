@@ -74,6 +74,11 @@ struct Params {
   int64_t* idx2;        // TOP2 kernels: runner-up code per latent (for the exact re-evaluation pass)
   long long* keys;
   PeerKeys peers;       // n > 0: MIN-combine the packed keys straight into every rank's buffer over NVLink
+  // EPI_STORE only: out (N x ldc) receives alpha * (z E^T) + bias for columns < K, zeros for columns in [K, ldc)
+  float* out;
+  int64_t ldc;
+  const float* bias;
+  float alpha;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -320,10 +325,18 @@ __device__ __forceinline__ void argmin_batch_top2(const uint32_t (&acc)[32], con
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------
-template <int CG, bool TOP2>
+// EPI selects what the epilogue warps do with each finished 128 x 256 accumulator tile:
+//   EPI_ARGMIN  running (min, index) per latent row                       -- the nearest-code search
+//   EPI_TOP2    the same, also keeping the runner-up and the tf32 score gap -- search for the exact re-evaluation
+//   EPI_STORE   out[row, col] = alpha * acc + bias[col]                   -- plain C = A B^T (the dense contractions of
+//               the Gumbel quantiser, models/shelgon3/GumbelQuantizer.py:55,64 and their backward)
+constexpr int EPI_ARGMIN = 0, EPI_TOP2 = 1, EPI_STORE = 2;
+
+template <int CG, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
                    const Params p) {
+  constexpr bool TOP2 = (EPI == EPI_TOP2);
   constexpr int B_ROWS = BLOCK_N / CG;                 // codebook rows this CTA loads per stage
   constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 4;  // 32 KB (CG=1) / 16 KB (CG=2)
 
@@ -483,6 +496,65 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
           if (elect_one()) tc_commit<CG>(bar_a_empty);        // latent tiles may be overwritten
           __syncwarp();
         }
+      }
+    }
+  } else if constexpr (EPI == EPI_STORE) {
+    // =========================== store epilogue (every CTA): C = alpha * A B^T + bias ===========================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;            // which 128 of the 256 accumulator columns
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int64_t item = first_item; item < p.n_items; item += item_stride) {
+      const int64_t m_group = item / p.ksplit;
+      const int ks = (int)(item % p.ksplit);
+      const int t_begin = ks * p.tiles_per_split;
+      const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+      const int64_t row = (m_group * CG + cta_rank) * BLOCK_M + row_in_tile;
+      float* orow = p.out + row * p.ldc;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(bar_tm_full + 8 * acc, acc_phase);
+        tc_fence_after();
+        const int64_t col0 = (int64_t)t * BLOCK_N + half * 128;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * 128;
+        uint32_t ra[32], rb[32];
+        auto store_batch = [&](const uint32_t (&r)[32], int64_t c0) {
+          if (row >= p.N) return;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int64_t c = c0 + j4 * 4;
+            if (c < p.ldc) {                      // ldc % 4 == 0: a float4 is wholly inside or outside the row
+              float4 o;
+              float* ov = reinterpret_cast<float*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float b = (p.bias && c + e < p.K) ? __ldg(p.bias + c + e) : 0.f;
+                ov[e] = (c + e < p.K) ? fmaf(p.alpha, __uint_as_float(r[j4 * 4 + e]), b) : 0.f;
+              }
+              *reinterpret_cast<float4*>(orow + c) = o;
+            }
+          }
+        };
+        tmem_ld32_async(taddr, ra);
+        tmem_wait_ld(ra);
+        tmem_ld32_async(taddr + 32, rb);
+        store_batch(ra, col0);
+        tmem_wait_ld(rb);
+        tmem_ld32_async(taddr + 64, ra);
+        store_batch(rb, col0 + 32);
+        tmem_wait_ld(ra);
+        tmem_ld32_async(taddr + 96, rb);
+        store_batch(ra, col0 + 64);
+        tmem_wait_ld(rb);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(map_to_cta(bar_tm_empty + 8 * acc, 0));
+          else mbar_arrive(bar_tm_empty + 8 * acc);
+        }
+        store_batch(rb, col0 + 96);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
@@ -657,7 +729,7 @@ static int env_int(const char* name, int dflt) {
   return (e && e[0]) ? atoi(e) : dflt;
 }
 
-template <int CG, bool TOP2>
+template <int CG, int EPI>
 static int launch_cg(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t k_offset,
                      int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st, const PeerKeys* peers,
                      int64_t* idx2) {
@@ -686,6 +758,8 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   p.use_atomic = (p.ksplit > 1 || keys_accumulate) ? 1 : 0;
   p.e2 = e2; p.idx = idx; p.keys = keys; p.idx2 = idx2;
   if (peers) p.peers = *peers; else p.peers.n = 0;
+  p.out = nullptr; p.ldc = 0; p.bias = nullptr; p.alpha = 1.f;
+  constexpr bool TOP2 = (EPI == EPI_TOP2);
   if (TOP2) KVQ_REQUIRE(p.ksplit == 1 && !p.use_atomic && p.peers.n == 0 && idx && idx2, KVQ_ERR_UNSUPPORTED,
                         "tf32 top-2 search needs an unsplit, unsharded search");
   KVQ_REQUIRE(p.peers.n > 0 || !p.use_atomic || keys, KVQ_ERR_ARG,
@@ -703,7 +777,7 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
     rc = launch_fill_keys(keys, N, st);
     if (rc) return rc;
   }
-  KVQ_CUDA(cudaFuncSetAttribute(search_tf32_kernel<CG, TOP2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KVQ_CUDA(cudaFuncSetAttribute(search_tf32_kernel<CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)(min_i64(p.n_items, groups) * CG);
   {
     ProfScope ps(KVQ_PROF_SEARCH, st);
@@ -720,14 +794,77 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     count_launch();
-    KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG, TOP2>, mz, me, p));
+    KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG, EPI>, mz, me, p));
   }
   // (also when the caller accumulates into its own key buffer: idx then reflects the merged keys, like the fp32 path)
   if (p.peers.n == 0 && p.use_atomic && idx) return launch_keys_to_idx(keys, N, idx, st);
   return KVQ_OK;
 }
 
+// C (M x ldc) = alpha * A (M x Kc) B^T (Ncols x Kc) + bias, tf32 products / fp32 accumulate; columns [Ncols, ldc) = 0.
+static int launch_store(const float* A, const float* B, int64_t M, int64_t Ncols, int Kc, float* C, int64_t ldc,
+                        const float* bias, float alpha, cudaStream_t st) {
+  constexpr int CG = 2;
+  constexpr int B_STAGE_BYTES = (BLOCK_N / CG) * BLOCK_K * 4;
+  Params p;
+  p.N = M; p.K = Ncols; p.k_offset = 0; p.D = Kc;
+  p.num_kblocks = Kc / BLOCK_K;
+  p.n_tiles = (int)((Ncols + BLOCK_N - 1) / BLOCK_N);
+  const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int64_t m_groups = (m_tiles + CG - 1) / CG;
+  const int groups = sm_count() / CG;
+  int ksplit = 1;
+  if (m_groups < groups) ksplit = (int)min_i64(p.n_tiles, (groups + m_groups - 1) / m_groups);
+  p.tiles_per_split = (p.n_tiles + ksplit - 1) / ksplit;
+  p.ksplit = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.n_items = m_groups * p.ksplit;
+  p.resident = (Kc <= RESIDENT_MAX_D) ? 1 : 0;
+  const int a_bytes = p.resident ? p.num_kblocks * A_KBLOCK_BYTES : 0;
+  const int stage_bytes = p.resident ? B_STAGE_BYTES : (A_KBLOCK_BYTES + B_STAGE_BYTES);
+  int stages = (SMEM_LIMIT - 1024 - SMEM_CTRL_BYTES - a_bytes) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  p.stages = stages;
+  p.use_atomic = 0;
+  p.e2 = nullptr; p.idx = nullptr; p.keys = nullptr; p.idx2 = nullptr;
+  p.peers.n = 0;
+  p.out = C; p.ldc = ldc; p.bias = bias; p.alpha = alpha;
+  const size_t smem = 1024 + SMEM_CTRL_BYTES + (size_t)a_bytes + (size_t)stages * stage_bytes;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, A, M, Kc, BLOCK_M, true);
+  if (rc) return rc;
+  rc = make_map(&mb, B, Ncols, Kc, BLOCK_N / CG, true);
+  if (rc) return rc;
+  KVQ_CUDA(cudaFuncSetAttribute(search_tf32_kernel<CG, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(min_i64(p.n_items, groups) * CG));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG, EPI_STORE>, ma, mb, p));
+  return KVQ_OK;
+}
+
 }  // namespace t5
+
+int launch_gemm_nt_tf32(const float* A, const float* B, int64_t M, int64_t Ncols, int Kc, float* C, int64_t ldc,
+                        const float* bias, float alpha, cudaStream_t st) {
+  if (M <= 0 || Ncols <= 0) return KVQ_OK;
+  KVQ_REQUIRE(Kc >= 32 && Kc % 32 == 0 && Kc <= 1 << 22, KVQ_ERR_SHAPE,
+              "kvq_gemm_nt: the contraction length must be a multiple of 32 (got %d)", Kc);
+  KVQ_REQUIRE(ldc >= Ncols && ldc % 4 == 0, KVQ_ERR_SHAPE, "kvq_gemm_nt: ldc=%lld must be >= n (%lld) and a multiple of 4",
+              (long long)ldc, (long long)Ncols);
+  KVQ_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0, KVQ_ERR_ARG, "kvq_gemm_nt: A, B, C must be 16-byte aligned");
+  KVQ_REQUIRE(M < (1ll << 31) - 256 && Ncols < (1ll << 31) - 256, KVQ_ERR_SHAPE, "kvq_gemm_nt: matrix too large");
+  return t5::launch_store(A, B, M, Ncols, Kc, C, ldc, bias, alpha, st);
+}
 
 bool tf32_shape_ok(int64_t N, int D, int64_t K) {
   return N > 0 && K > 0 && D >= 32 && D % 32 == 0 && D <= 4096 && N < (1ll << 31) - 256 && K < (1ll << 31) - 256;
@@ -742,8 +879,8 @@ int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t 
   KVQ_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)E & 15) == 0, KVQ_ERR_ARG,
               "tf32 search needs 16-byte aligned z and E (TMA)");
   static const int cta_group = t5::env_int("KVQ_TF32_CTA_GROUP", 2);
-  if (cta_group == 1) return t5::launch_cg<1, false>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers, nullptr);
-  return t5::launch_cg<2, false>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers, nullptr);
+  if (cta_group == 1) return t5::launch_cg<1, t5::EPI_ARGMIN>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers, nullptr);
+  return t5::launch_cg<2, t5::EPI_ARGMIN>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers, nullptr);
 }
 
 // Would the tensor-core search split the code range over CTAs for this shape?  (Then the top-2 variant is not used.)
@@ -758,7 +895,7 @@ int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int
   KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (got D=%d)", D);
   KVQ_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)E & 15) == 0, KVQ_ERR_ARG,
               "tf32 search needs 16-byte aligned z and E (TMA)");
-  return t5::launch_cg<2, true>(z, E, e2, N, D, K, 0, idx, nullptr, 0, st, nullptr, idx2);
+  return t5::launch_cg<2, t5::EPI_TOP2>(z, E, e2, N, D, K, 0, idx, nullptr, 0, st, nullptr, idx2);
 }
 
 }  // namespace kvq

@@ -295,3 +295,42 @@ class LiteralVectorQuantizer(torch.nn.Module):
         usage = torch.mean(hot, dim=0)
         perplexity = torch.exp(-torch.sum(usage * torch.log(usage + 1e-10)))
         return loss, out, perplexity, hot, nearest.reshape(z.shape[0], z.shape[1], 1)
+
+
+# ---- GumbelQuantizer (models/shelgon3/GumbelQuantizer.py:43-83), the alternative VQ_MODE -----------------------------
+
+def gumbel_noise_like_reference(shape_bks, seed: int) -> torch.Tensor:
+    """The Gumbel(0,1) sample F.gumbel_softmax draws for logits of shape (B, K, S) right after torch.manual_seed(seed)
+    (torch/nn/functional.py: `-torch.empty_like(logits).exponential_().log()`), returned in (B, S, K) layout."""
+    torch.manual_seed(seed)
+    g = -torch.empty(shape_bks, dtype=torch.float32).exponential_().log()
+    return g.permute(0, 2, 1).contiguous()
+
+
+def gumbel_forward(z: torch.Tensor, W: torch.Tensor, b: torch.Tensor, E: torch.Tensor, noise: torch.Tensor, tau: float,
+                   kld_scale: float, hard: bool):
+    """GumbelQuantizer.forward restated on (B, S, .) row-major tensors with the Gumbel sample given explicitly.
+
+      z (B,S,C), W (K,C) = proj.weight[:, :, 0], b (K) = proj.bias, E (K,D) = embed.weight, noise (B,S,K)
+      logits = z W^T + b                                   :55  (1x1 Conv1d over the channel axis)
+      y_soft = softmax((logits + noise) / tau) over K      :57  (F.gumbel_softmax)
+      y      = one_hot(argmax y_soft) - sg(y_soft) + y_soft  if hard else y_soft
+      z_q    = y E                                         :64  (einsum 'b n s, n d -> b d s')
+      qy     = softmax(logits);  diff = kld_scale * mean_{b,s} sum_k qy log(qy K + 1e-10)      :68-71
+      ind    = argmax_k y                                  :74
+    Differentiable torch code: autograd of this function is the backward oracle."""
+    K = W.shape[0]
+    logits = torch.matmul(z, W.t()) + b
+    gum = (logits + noise) / tau
+    y_soft = gum.softmax(dim=-1)
+    if hard:
+        index = y_soft.max(dim=-1, keepdim=True)[1]
+        y_hard = torch.zeros_like(logits).scatter_(-1, index, 1.0)
+        y = y_hard - y_soft.detach() + y_soft
+    else:
+        y = y_soft
+    z_q = torch.matmul(y, E)
+    qy = torch.softmax(logits, dim=-1)
+    diff = kld_scale * torch.sum(qy * torch.log(qy * K + 1e-10), dim=-1).mean()
+    ind = y.argmax(dim=-1)
+    return z_q, diff, ind

@@ -108,5 +108,43 @@ def main():
     np.savez_compressed(os.path.join(HERE, "seq_acc.npz"), a=a.numpy(), b=b.numpy(), acc=acc.numpy(), per=per.numpy())
 
 
+def gumbel_goldens():
+    """GumbelQuantizer (models/shelgon3/GumbelQuantizer.py): the unmodified class, with torch's RNG seeded right before
+    the forward so that the Gumbel sample F.gumbel_softmax draws can be reproduced and stored next to the outputs."""
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from GumbelQuantizer import GumbelQuantizer
+    from oracle.vq_oracle import gumbel_noise_like_reference
+    torch.set_num_threads(1)
+    cases = [  # name, B, S, C, K, D, tau, kld_scale, straight_through, is_training, seed
+        ("soft", 4, 12, 64, 32, 64, 0.9, 5e-4, False, True, 81),
+        ("hard", 4, 12, 64, 32, 64, 1.0, 5e-4, True, True, 82),
+        ("eval", 2, 12, 96, 9, 32, 0.5, 1e-3, False, False, 83),      # eval forces hard=True; K=9 as in the analyses
+    ]
+    for name, B, S, C, K, D, tau, kld, st, train, seed in cases:
+        g = torch.Generator().manual_seed(seed)
+        z = torch.randn(B, S, C, generator=g)
+        gz = torch.randn(B, S, D, generator=g)
+        torch.manual_seed(seed)
+        gq = GumbelQuantizer(enc_out_size=C, n_embed=K, embedding_dim=D, temperature=tau, kl_div_scale=kld, straight_through=st)
+        zin = z.clone().requires_grad_(True)
+        noise = gumbel_noise_like_reference((B, K, S), seed + 1000)
+        torch.manual_seed(seed + 1000)
+        z_q, diff, ind = gq.forward(zin, train)
+        (diff * 3.0 + (z_q * gz).sum()).backward()
+        np.savez_compressed(
+            os.path.join(HERE, f"gumbel_{name}.npz"),
+            z=z.numpy(), gz=gz.numpy(), W=gq.proj.weight.detach()[:, :, 0].numpy(), b=gq.proj.bias.detach().numpy(),
+            E=gq.embed.weight.detach().numpy(), noise=noise.numpy(), tau=np.float64(tau), kld_scale=np.float64(kld),
+            hard=np.bool_(st if train else True), w=np.float64(3.0),
+            z_q=z_q.detach().numpy(), diff=diff.detach().numpy(), ind=ind.numpy(), dz=zin.grad.numpy(),
+            dW=gq.proj.weight.grad[:, :, 0].numpy(), db=gq.proj.bias.grad.numpy(), dE=gq.embed.weight.grad.numpy())
+        print("gumbel", name, "diff", float(diff), "unique codes", int(ind.unique().numel()))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "gumbel":
+        gumbel_goldens()
+    else:
+        main()
+        gumbel_goldens()

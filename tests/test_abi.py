@@ -58,6 +58,9 @@ def test_pack_key_orders_by_score_then_index(lib):
     assert f(-0.0, 7) == f(0.0, 7)                             # -0 and +0 compare equal as floats
     assert f(2.0, 0) > f(1.0, 0xFFFFFFFF)                      # score dominates index
     assert f(1.0, 123456) & 0xFFFFFFFF == 123456
+    # torch.argmin treats NaN as the minimum (VectorQuantizer.py:65): a NaN score packs below -inf, lowest index first
+    nan = float("nan")
+    assert f(nan, 5) < f(-float("inf"), 0) and f(nan, 5) < f(nan, 6) and f(-nan, 5) == f(nan, 5)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")

@@ -87,7 +87,9 @@ def test_fused_recon_loss_matches_the_reference_expressions(B, S, V, scale):
     loss_scaled.backward()
     torch.cuda.synchronize()
     assert torch.equal(recon, recon_r)
-    assert float(acc) == float(acc_r) and torch.equal(per, per_r)
+    # torch forms sum / numel as sum * (1 / numel) on CUDA and as a true division on the CPU: allow that last-bit difference
+    assert abs(float(acc) - float(acc_r)) <= 1.2e-7 and float((per - per_r).abs().max()) <= 1.2e-7
+    assert abs(float(acc) - float(((recon_r - ids) == 0).sum()) / recon_r.numel()) <= 6e-8
     assert abs(float(loss) - float(loss_r)) <= 2e-6 * abs(float(loss_r)) + 1e-7
     assert float((logits.grad - grad_r).abs().max()) <= 1e-5 * float(grad_r.abs().max()) + 1e-10
     # bitwise reproducible (fixed-order reduction of the row losses)
@@ -112,6 +114,6 @@ def test_recon_loss_inplace_scaling_and_compile():
     torch._dynamo.reset()
     l_c, r_c, a_c = torch.compile(step, fullgraph=True, backend="aot_eager")(logits)
     l_c.backward()
-    assert torch.equal(r_c, r_e) and float(a_c) == float(a_e)
+    assert torch.equal(r_c, r_e) and float(a_c) == float(a_e)   # same kernel both times
     assert abs(float(l_c) - float(l_e)) <= 1e-6 * float(l_e)
     assert torch.allclose(logits.grad, g_e, rtol=1e-5, atol=1e-9)

@@ -91,3 +91,23 @@ def test_kshard_merge_equals_global_argmin():
         idx = O.kshard_merge(g["z"], g["E"], shards)
         par = O.index_parity(idx, g["idx"], g["z"], g["E"], exact_fp32=True)
         assert par.unexcused == 0
+
+
+@pytest.mark.parametrize("name", ["soft", "hard", "eval"])
+def test_gumbel_oracle_matches_the_reference_class(name):
+    """oracle.gumbel_forward (+ its autograd) against fixtures produced by the unmodified GumbelQuantizer
+    (models/shelgon3/GumbelQuantizer.py:43-83) with torch's RNG seeded so that the Gumbel sample is the stored one."""
+    d = np.load(os.path.join(GOLDEN, f"gumbel_{name}.npz"))
+    t = {k: torch.from_numpy(np.array(d[k])) for k in d.files}
+    z = t["z"].clone().requires_grad_(True)
+    W = t["W"].clone().requires_grad_(True)
+    b = t["b"].clone().requires_grad_(True)
+    E = t["E"].clone().requires_grad_(True)
+    z_q, diff, ind = O.gumbel_forward(z, W, b, E, t["noise"], float(t["tau"]), float(t["kld_scale"]), bool(t["hard"]))
+    (diff * float(t["w"]) + (z_q * t["gz"]).sum()).backward()
+    assert torch.equal(ind, t["ind"])
+    assert torch.allclose(z_q, t["z_q"], rtol=1e-5, atol=1e-6)
+    assert abs(float(diff) - float(t["diff"])) <= 1e-5 * abs(float(t["diff"]))
+    for got, key in ((z.grad, "dz"), (W.grad, "dW"), (b.grad, "db"), (E.grad, "dE")):
+        ref = t[key]
+        assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-9, key
