@@ -57,3 +57,31 @@ def vq_words_distrib(table: torch.Tensor, token_id_to_word: Mapping[int, str]) -
         if words:
             out[k] = words
     return out
+
+
+def write_results(results_dir: str, table: torch.Tensor, word_to_token_id: Mapping[str, int],
+                  token_id_to_word: Mapping[int, str]) -> Dict[str, str]:
+    """Write the three result files of the reference analysis, same names and schema
+    (analyses/unsupervised_vq_disentanglement/unsupervised_vq_disentanglement.py:206-235):
+
+      dSentences_vq_vector_populated.txt            "the following VQ latent vectors were populated: {set}"      (:209-210)
+      dSentences_words_of_interest_histograms.json  {word: {code: count}}, every code present                      (:212-226)
+      dSentences_vq_words_distrib.json              {code: [distinct words mapped to it]}                          (:228-235)
+
+    json.dump turns the integer code keys into strings, exactly as it does for the reference's dicts.
+    Returns {name: path}."""
+    import json
+    import os
+    os.makedirs(results_dir, exist_ok=True)
+    paths = {
+        "populated": os.path.join(results_dir, "dSentences_vq_vector_populated.txt"),
+        "histograms": os.path.join(results_dir, "dSentences_words_of_interest_histograms.json"),
+        "distrib": os.path.join(results_dir, "dSentences_vq_words_distrib.json"),
+    }
+    with open(paths["populated"], "w") as f:
+        f.write(f"the following VQ latent vectors were populated: {str(populated_codes(table))}")
+    with open(paths["histograms"], "w") as fp:
+        json.dump(words_of_interest_histograms(table, word_to_token_id), fp)
+    with open(paths["distrib"], "w") as fp:
+        json.dump(vq_words_distrib(table, token_id_to_word), fp)
+    return paths

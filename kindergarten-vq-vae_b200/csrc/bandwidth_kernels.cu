@@ -71,15 +71,21 @@ int launch_keys_to_idx(const long long* keys, int64_t N, int64_t* idx, cudaStrea
 // exact re-evaluation of the tensor-core search's two best candidates ("tf32_refine" search mode).
 //
 // The TOP2 search leaves, per latent, the winner a (idx) and a packed word (idx2): runner-up b in the low half, the
-// tf32 score gap s_b - s_a in the high half.  Both tf32 scores carry an operand-rounding error of at most
-// 2^-9 |z_i| |E_k| (two products of operands rounded to 11 significant bits, Cauchy-Schwarz), so the pair can only be
-// mis-ordered when   gap <= tau_i = 2^-7 |z_i| max_k|E_k| + 2^-16 max_k|E_k|^2
-// (twice the rigorous bound, plus the fp32 rounding of the norms and of the accumulation).  Rows inside the bound
-// get |z - E_a|^2 and |z - E_b|^2 accumulated in float64 from the fp32 inputs (exact differences): the smaller
-// distance wins, ties go to the lower index.  Rows outside the bound keep a: the tf32 order is provably the exact one.
+// tf32 score gap s_b - s_a in the high half.  Each tf32 score carries an operand-rounding error of at most
+// 2^-9 |z_i| |E_k| (the dot product of operands rounded to nearest at 11 significant bits: relative error
+// 2^-11 + 2^-11 per product, Cauchy-Schwarz over the sum, times the factor 2 of the score), so the pair can only be
+// mis-ordered when   gap <= tau_i = c |z_i| max_k|E_k| + 2^-16 max_k|E_k|^2,   c = 1.125 * 2^-8
+// (both scores' bounds, 12.5 % slack for the fp32 accumulation of up to 1024 products; the second term covers the fp32
+// rounding of the norms and of the final fma; c doubles when the operands are truncated instead of rounded).
+// Rows inside the bound get |z - E_a|^2 and |z - E_b|^2 accumulated in float64 from the fp32 inputs (exact
+// differences): the smaller distance wins, ties go to the lower index.  Rows outside the bound keep a: there the tf32
+// order is provably the exact one.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float refine_threshold(float z2, float e2max) {
-  return 0.0078125f * sqrtf(z2 * e2max) + 1.52587890625e-5f * e2max;
+// gap inside the bound?  (written without a square root: t = gap - 2^-16 e2max; inside iff t <= 0 or t^2 <= c^2 z2 e2max;
+// a NaN anywhere -- NaN winner, non-finite norms -- counts as inside)
+__device__ __forceinline__ bool refine_inside_bound(float gap, float z2, float e2max, float c2) {
+  const float t = fmaf(-1.52587890625e-5f, e2max, gap);
+  return !(t > 0.f && t * t > c2 * z2 * e2max);
 }
 __device__ __forceinline__ double sqdiff4(const float4& x, const float4& p) {
   double t, s;
@@ -94,7 +100,7 @@ __device__ __forceinline__ double sqdiff4(const float4& x, const float4& p) {
 __global__ void __launch_bounds__(256) refine_top2_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                           int64_t N, int D, int64_t* __restrict__ idx,
                                                           const int64_t* __restrict__ idx2,
-                                                          const float* __restrict__ e2max_p) {
+                                                          const float* __restrict__ e2max_p, float c2) {
   constexpr int R = 4;   // latents per warp, all their loads issued before the first use (memory-level parallelism)
   const int lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
@@ -137,16 +143,23 @@ __global__ void __launch_bounds__(256) refine_top2_kernel(const float* __restric
   for (int r = 0; r < R; ++r) {
     const double sa = warp_sum(da[r]), sb = warp_sum(db[r]);
     const float zz = warp_sum(z2[r]);
-    const bool close = !(gap[r] > refine_threshold(zz, e2max));
+    const bool close = refine_inside_bound(gap[r], zz, e2max, c2);
     if (lane == 0 && row0 + r < N && close && a[r] != b[r] && (sb < sa || (sb == sa && b[r] < a[r]))) idx[row0 + r] = b[r];
   }
+}
+
+// squared coefficient c^2 of the error bound: operands rounded to nearest by the TMA unit (default) or truncated by the MMA
+static float refine_bound_c2() {
+  const float c = 1.125f * 0.00390625f * (tf32_operands_rounded() ? 1.f : 2.f);
+  return c * c;
 }
 
 int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2,
                        const float* e2max, cudaStream_t st) {
   if (N <= 0) return KVQ_OK;
   const int rows_per_block = 8 * 4;   // 8 warps x 4 latents
-  refine_top2_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(z, E, N, D, idx, idx2, e2max);
+  refine_top2_kernel<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(z, E, N, D, idx, idx2, e2max,
+                                                                                           refine_bound_c2());
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }
@@ -264,7 +277,7 @@ template <int VPL>
 __global__ void __launch_bounds__(QR_WPB * 32, (VPL <= 4) ? 2 : 1) quantize_refine_kernel(
     const float* __restrict__ z, const float* __restrict__ E, int64_t* __restrict__ idx, const int64_t* __restrict__ idx2,
     const float* __restrict__ e2max_p, int64_t N, int D, int64_t K, float* __restrict__ z_q, double* __restrict__ sq_sum,
-    int32_t* __restrict__ hist, int rows_per_warp, int stages) {
+    int32_t* __restrict__ hist, int rows_per_warp, int stages, float c2) {
   extern __shared__ __align__(128) uint8_t qr_smem[];
   __shared__ double part[QR_WPB];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -344,7 +357,7 @@ __global__ void __launch_bounds__(QR_WPB * 32, (VPL <= 4) ? 2 : 1) quantize_refi
       if (r + stages < count) issue(r + stages, s, r >> 5);
       if (++s == stages) { s = 0; phase ^= 1; }
       z2 = warp_sum(z2);
-      if (b < K && b != a && !(gap > refine_threshold(z2, e2max))) {     // warp-uniform: inside the tf32 error bound
+      if (b < K && b != a && refine_inside_bound(gap, z2, e2max, c2)) {   // warp-uniform: inside the tf32 error bound
         const float4* br = reinterpret_cast<const float4*>(E + b * (int64_t)D);
         float4 bv[VPL];
         double da = 0.0, db = 0.0;
@@ -422,13 +435,14 @@ static int launch_quantize_refine(const float* z, const float* E, int64_t* idx, 
   const int64_t n_warps = chunks < max_warps ? chunks : max_warps;
   const int rows_per_warp = (int)(((N + n_warps - 1) / n_warps + 31) / 32 * 32);
   const unsigned blocks = (unsigned)((n_warps + QR_WPB - 1) / QR_WPB);
+  const float c2 = refine_bound_c2();
   KVQ_REQUIRE((((uintptr_t)z | (uintptr_t)E | (uintptr_t)z_q) & 15) == 0, KVQ_ERR_ARG,
               "kvq_forward: z, E and z_q must be 16-byte aligned (128-bit / bulk-copy accesses)");
 #define KVQ_QR(V)                                                                                                       \
   case V:                                                                                                               \
     KVQ_CUDA(cudaFuncSetAttribute(quantize_refine_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
     quantize_refine_kernel<V><<<blocks, QR_WPB * 32, smem, st>>>(z, E, idx, idx2, e2max, N, D, K, z_q, sq_sum, hist,      \
-                                                                 rows_per_warp, stages);                                \
+                                                                 rows_per_warp, stages, c2);                            \
     break;
   switch (vpl) {
     KVQ_QR(1) KVQ_QR(2) KVQ_QR(3) KVQ_QR(4) KVQ_QR(5) KVQ_QR(6) KVQ_QR(7) KVQ_QR(8)

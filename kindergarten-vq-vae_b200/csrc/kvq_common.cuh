@@ -175,6 +175,7 @@ int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t 
                        const PeerKeys* peers = nullptr);
 bool tf32_shape_ok(int64_t N, int D, int64_t K);
 bool tf32_search_splits(int64_t N, int64_t K);
+bool tf32_operands_rounded();   // TMA rounds fp32 -> tf32 to nearest (default) instead of the MMA truncating
 int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
                             int64_t* idx, int64_t* idx2, cudaStream_t st);
 int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2,

@@ -766,7 +766,7 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
               "kvq_search(tf32): split/accumulate search needs a keys buffer");
   const size_t smem = 1024 + SMEM_CTRL_BYTES + (size_t)a_bytes + (size_t)stages * stage_bytes;
 
-  static const bool round_tf32 = env_int("KVQ_TMA_ROUND_TF32", 1) != 0;
+  const bool round_tf32 = tf32_operands_rounded();
   CUtensorMap mz, me;
   int rc = make_map(&mz, z, N, D, BLOCK_M, round_tf32);
   if (rc) return rc;
@@ -864,6 +864,11 @@ int launch_gemm_nt_tf32(const float* A, const float* B, int64_t M, int64_t Ncols
   KVQ_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0, KVQ_ERR_ARG, "kvq_gemm_nt: A, B, C must be 16-byte aligned");
   KVQ_REQUIRE(M < (1ll << 31) - 256 && Ncols < (1ll << 31) - 256, KVQ_ERR_SHAPE, "kvq_gemm_nt: matrix too large");
   return t5::launch_store(A, B, M, Ncols, Kc, C, ldc, bias, alpha, st);
+}
+
+bool tf32_operands_rounded() {
+  static const bool rounded = t5::env_int("KVQ_TMA_ROUND_TF32", 1) != 0;
+  return rounded;
 }
 
 bool tf32_shape_ok(int64_t N, int D, int64_t K) {

@@ -174,3 +174,34 @@ def test_code_usage_analysis_matches_python_loops():
     distrib = A.vq_words_distrib(table, words)
     assert {c: sorted(v) for c, v in per_code.items()} == distrib
     assert int(table.sum()) == 2 * B * S
+
+
+def test_code_usage_result_files_have_the_reference_schema(tmp_path):
+    """analysis.write_results: the three files of unsupervised_vq_disentanglement.py:206-235, same names and JSON layout."""
+    import json
+    k = _kvq()
+    A = k.analysis
+    gen = torch.Generator().manual_seed(10)
+    B, S, V, K = 32, 12, 40, 9
+    ids = torch.randint(0, V, (B, S), generator=gen)
+    codes = torch.randint(0, K, (B, S, 1), generator=gen)
+    table = A.code_usage_by_token(ids.to(DEV), codes.to(DEV), V, K)
+    words = {t: f"w{t}" for t in range(V)}
+    interest = {"w1": 1, "w2": 2}
+    paths = A.write_results(str(tmp_path / "run"), table, interest, words)
+    assert sorted(os.path.basename(p) for p in paths.values()) == [
+        "dSentences_vq_vector_populated.txt", "dSentences_vq_words_distrib.json", "dSentences_words_of_interest_histograms.json"]
+    txt = open(paths["populated"]).read()
+    assert txt.startswith("the following VQ latent vectors were populated: {")
+    # the reference builds the same dicts with Python loops and json.dump()s them: integer keys become strings
+    per_word = {w: [] for w in interest}
+    per_code = {}
+    for row_ids, row_codes in zip(ids.tolist(), codes.flatten(1).tolist()):
+        for t, c in zip(row_ids, row_codes):
+            per_code.setdefault(c, set()).add(words[t])
+            if words[t] in interest:
+                per_word[words[t]].append(c)
+    ref_hist = json.loads(json.dumps({w: {c: per_word[w].count(c) for c in range(9)} for w in interest}))
+    assert json.load(open(paths["histograms"])) == ref_hist
+    got = json.load(open(paths["distrib"]))
+    assert {c: sorted(v) for c, v in got.items()} == {str(c): sorted(v) for c, v in per_code.items()}
