@@ -335,6 +335,28 @@ def run_kvq(args):
     ms_per_step = float(t.item()) / args.steps
     value = n_rows * world / (ms_per_step * 1e-3)
 
+    # ---- where the multi-GPU step time goes: per-rank spread (the headline is the MAX over ranks) and the bare cost of
+    #      the one large collective (all-reduce of the 64 MiB codebook gradient) ----------------------------------------
+    dp_breakdown = None
+    if world > 1:
+        mine = torch.tensor([total_ms / args.steps, prof["search"] or 0.0], device=dev, dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        buf = torch.empty(K, D, device=dev)
+        for _ in range(2):
+            dist.all_reduce(buf)
+        torch.cuda.synchronize(); dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            dist.all_reduce(buf)
+        a1.record(); torch.cuda.synchronize()
+        dp_breakdown = {"ms_per_step_by_rank": [float(x[0]) for x in allr], "search_ms_by_rank": [float(x[1]) for x in allr],
+                        "allreduce_dE_ms": a0.elapsed_time(a1) / 5, "allreduce_bytes": K * D * 4,
+                        "note": "ms_per_step is the max over ranks: the spread between GPUs of the power-capped search kernel "
+                                "and the unoverlapped dE all-reduce are the two terms that separate N-GPU from 1-GPU step time"}
+        del buf
+
     idx_timed = last["idx"].reshape(-1).clone()       # the indices the LAST TIMED step produced (default search mode)
     dE_timed = vq.embedding.weight.grad.detach().clone()
 
@@ -514,7 +536,7 @@ def run_kvq(args):
                        "codebook_init": "data-scale: N(0,1) rows + 0.1 noise"},
             "roofline": roof, "roofline_other_kernels": others, "kernel_ms": prof,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "kshard": kshard, "dp_dE_check": dp_check, "host_placement": numa, "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp),
+            "kshard": kshard, "dp_dE_check": dp_check, "dp_breakdown": dp_breakdown, "host_placement": numa, "clocks": clocks, "loss": float(loss.detach()), "perplexity": float(perp),
             "search_mode": search_mode, "index_parity": parity, "plain_tf32_beside": refine, "reference_cuda": ref_cuda,
         }
         print(json.dumps(line), flush=True)

@@ -145,6 +145,13 @@ int kvq_forward(const float* z, const float* E, int64_t N, int D, int64_t K, flo
 int kvq_forward_partials(const float* z, const float* E, int64_t N, int D, int64_t K, int mode, float* z_q, int64_t* idx,
                          double* sq_sum, int32_t* hist, void* workspace, size_t workspace_bytes, kvq_stream_t stream);
 
+/* The two partials packed into ONE float64 buffer of 1 + K entries (packed[0] = sq_sum, packed[1 + k] = hist[k]; counts are
+ * exact in float64) so that a single all-reduce(SUM) carries them, and the finalisation from the reduced buffer:
+ * loss / perplexity as kvq_finalize, hist_out (K int32, may be NULL) = the global usage counts. */
+int kvq_pack_partials(const double* sq_sum, const int32_t* hist, int64_t K, double* packed, kvq_stream_t stream);
+int kvq_finalize_packed(const double* packed, int64_t n_global, int D, int64_t K, float beta, float* loss, float* perplexity,
+                        int32_t* hist_out, kvq_stream_t stream);
+
 /* Backward of the layer (what autograd derives from VectorQuantizer.py:72-80):
  *   dz[i]  = g_zq[i] + g_loss * 2 (z_i - q_i) / (n_global D)
  *   dE[k]  = g_loss * beta * 2 / (n_global D) * sum_{i: idx_i = k} (q_i - z_i)      dense, exact zeros elsewhere

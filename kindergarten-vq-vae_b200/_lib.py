@@ -38,6 +38,8 @@ SIGNATURES = {
     "kvq_finalize": (c_int, [_P, _P, c_int64, c_int, c_int64, c_float, _P, _P, _P]),
     "kvq_forward": (c_int, [_P, _P, c_int64, c_int, c_int64, c_float, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "kvq_forward_partials": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "kvq_pack_partials": (c_int, [_P, _P, c_int64, _P, _P]),
+    "kvq_finalize_packed": (c_int, [_P, c_int64, c_int, c_int64, c_float, _P, _P, _P, _P]),
     "kvq_backward": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_int64, c_float, c_int64, _P, _P,
                              _P, c_size_t, _P]),
     "kvq_backward_peers": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_float, c_int64, _P, _P, _P, c_int,

@@ -307,6 +307,19 @@ static int forward_partials(const char* who, const float* z, const float* E, int
   return rc;
 }
 
+int kvq_pack_partials(const double* sq_sum, const int32_t* hist, int64_t K, double* packed, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  KVQ_REQUIRE(sq_sum && hist && packed && K >= 1, KVQ_ERR_ARG, "kvq_pack_partials: bad arguments");
+  return launch_pack_partials(sq_sum, hist, K, packed, (cudaStream_t)stream);
+}
+
+int kvq_finalize_packed(const double* packed, int64_t n_global, int D, int64_t K, float beta, float* loss, float* perplexity,
+                        int32_t* hist_out, kvq_stream_t stream) {
+  int rc = check_device(); if (rc) return rc;
+  KVQ_REQUIRE(packed && loss && perplexity && n_global > 0 && D > 0 && K > 0, KVQ_ERR_ARG, "kvq_finalize_packed: bad arguments");
+  return launch_finalize_packed(packed, n_global, D, K, beta, loss, perplexity, hist_out, (cudaStream_t)stream);
+}
+
 int kvq_forward(const float* z, const float* E, int64_t N, int D, int64_t K, float beta, int mode, float* z_q,
                 int64_t* idx, float* loss, float* perplexity, int32_t* hist, void* ws, size_t ws_bytes,
                 kvq_stream_t stream) {

@@ -511,6 +511,49 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
   }
 }
 
+// Batch-sharded layer: the two per-rank partials that the loss / perplexity need, packed into ONE float64 buffer
+// (counts are exact in float64) so that a single all-reduce(SUM) moves them; and the finalisation reading that buffer.
+__global__ void __launch_bounds__(256) pack_partials_kernel(const double* __restrict__ sq_sum, const int32_t* __restrict__ hist,
+                                                            int64_t K, double* __restrict__ packed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) packed[0] = *sq_sum;
+  if (i < K) packed[1 + i] = (double)hist[i];
+}
+__global__ void __launch_bounds__(1024) finalize_packed_kernel(const double* __restrict__ packed, int64_t n_global, int D,
+                                                               int64_t K, float beta, float* __restrict__ loss,
+                                                               float* __restrict__ perplexity, int32_t* __restrict__ hist_out) {
+  __shared__ double part[32];
+  const float n_f = (float)n_global;
+  double s = 0.0;
+  for (int64_t k = threadIdx.x; k < K; k += blockDim.x) {
+    const int32_t c = (int32_t)packed[1 + k];
+    if (hist_out) hist_out[k] = c;
+    const float p = (float)c / n_f;
+    s += (double)(p * logf(p + 1e-10f));
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+    *perplexity = expf(-(float)t);
+    const float m = (float)(packed[0] / ((double)n_global * (double)D));
+    *loss = m + beta * m;
+  }
+}
+int launch_pack_partials(const double* sq_sum, const int32_t* hist, int64_t K, double* packed, cudaStream_t st) {
+  pack_partials_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(sq_sum, hist, K, packed);
+  KVQ_LAUNCH_CHECK();
+  return KVQ_OK;
+}
+int launch_finalize_packed(const double* packed, int64_t n_global, int D, int64_t K, float beta, float* loss,
+                           float* perplexity, int32_t* hist_out, cudaStream_t st) {
+  finalize_packed_kernel<<<1, 1024, 0, st>>>(packed, n_global, D, K, beta, loss, perplexity, hist_out);
+  KVQ_LAUNCH_CHECK();
+  return KVQ_OK;
+}
+
 int launch_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, int D, int64_t K, float beta,
                     float* loss, float* perplexity, cudaStream_t st) {
   finalize_kernel<<<1, 1024, 0, st>>>(sq_sum, hist, n_global, D, K, beta, loss, perplexity);

@@ -196,6 +196,9 @@ int launch_quantize(const float* z, const float* E, int64_t* idx, int64_t N, int
                     const ShardPtrs* shards = nullptr, const int64_t* idx2 = nullptr, const float* e2max = nullptr);
 int launch_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, int D, int64_t K, float beta,
                     float* loss, float* perplexity, cudaStream_t st);
+int launch_pack_partials(const double* sq_sum, const int32_t* hist, int64_t K, double* packed, cudaStream_t st);
+int launch_finalize_packed(const double* packed, int64_t n_global, int D, int64_t K, float beta, float* loss,
+                           float* perplexity, int32_t* hist_out, cudaStream_t st);
 int launch_backward(const float* z, const float* E, const int64_t* idx, const int32_t* hist, const float* g_zq,
                     const float* g_loss, int64_t N, int D, int64_t K, int64_t k_offset, float beta,
                     int64_t n_global, float* dz, float* dE, void* ws, size_t ws_bytes, cudaStream_t st,

@@ -159,6 +159,29 @@ def vq_forward_partials(z: torch.Tensor, E: torch.Tensor, *, mode: str = "auto",
     return z_q, idx, sq_sum, hist
 
 
+def pack_partials(sq_sum: torch.Tensor, hist: torch.Tensor) -> torch.Tensor:
+    """[sq_sum | hist] as one float64 buffer of 1 + K entries: the batch-sharded forward all-reduces this once."""
+    _req(sq_sum, "sq_sum", torch.float64); _req(hist, "hist", torch.int32)
+    K = hist.numel()
+    packed = torch.empty(K + 1, dtype=torch.float64, device=hist.device)
+    with torch.cuda.device(hist.device):
+        check(_lib.load().kvq_pack_partials(sq_sum.data_ptr(), hist.data_ptr(), K, packed.data_ptr(), _stream()),
+              "kvq_pack_partials")
+    return packed
+
+
+def finalize_packed(packed: torch.Tensor, n_global: int, D: int, beta: float):
+    """loss, perplexity and the global usage histogram from the all-reduced buffer of `pack_partials`."""
+    _req(packed, "packed", torch.float64)
+    K = packed.numel() - 1
+    out = torch.empty(2, dtype=torch.float32, device=packed.device)
+    hist = torch.empty(K, dtype=torch.int32, device=packed.device)
+    with torch.cuda.device(packed.device):
+        check(_lib.load().kvq_finalize_packed(packed.data_ptr(), n_global, D, K, beta, out.data_ptr(), out.data_ptr() + 4,
+                                              hist.data_ptr(), _stream()), "kvq_finalize_packed")
+    return out[0], out[1], hist
+
+
 def vq_backward(z: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, hist: Optional[torch.Tensor], beta: float, *,
                 g_zq: Optional[torch.Tensor] = None, g_loss: Optional[torch.Tensor] = None, need_dz: bool = True,
                 need_dE: bool = True, k_offset: int = 0, n_global: Optional[int] = None,

@@ -43,18 +43,6 @@ def z_is_cuda(device) -> bool:
     return torch.device(device).type == "cuda"
 
 
-def _all_reduce_together(tensors, group, device) -> None:
-    """SUM-all-reduce several small tensors of different dtypes as ONE NCCL group launch."""
-    cm = getattr(dist, "_coalescing_manager", None)
-    if cm is not None and torch.device(device).type == "cuda":
-        with cm(group=group, device=torch.device(device), async_ops=False):
-            for t in tensors:
-                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        return
-    for t in tensors:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-
-
 def shard_bounds(total: int, parts: int, part: int):
     """Contiguous equal shards (the last may be short): [lo, hi) of shard `part`."""
     per = (total + parts - 1) // parts
@@ -83,11 +71,11 @@ class _BatchShardedFn(torch.autograd.Function):
         # local forward of the layer with the default search machinery (incl. the fused exact top-2 re-evaluation);
         # its loss / perplexity are per-rank values and are recomputed below from the all-reduced partials
         z_q, idx, sq_sum, hist_local = F.vq_forward_partials(z, E, mode=mode)
-        hist = hist_local.clone()
+        # the two partials the loss / perplexity need (8 B and 4K B) travel as ONE float64 buffer: one all-reduce
+        packed = F.pack_partials(sq_sum, hist_local)
         if _world(group) > 1:
-            # the two partials the loss / perplexity need (8 B and 4K B): ONE coalesced NCCL launch
-            _all_reduce_together([sq_sum, hist], group, z.device)
-        loss, perplexity = F.finalize(sq_sum, hist, n_global, D, beta)
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        loss, perplexity, hist = F.finalize_packed(packed, n_global, D, beta)
         loss, perplexity = loss.clone(), perplexity.clone()
         ctx.save_for_backward(z, E, idx, hist_local)
         ctx.beta, ctx.group, ctx.n_global, ctx.grad_peer = beta, group, n_global, grad_peer

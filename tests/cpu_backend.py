@@ -36,6 +36,16 @@ def vq_forward_partials(z, E, *, mode="auto", ws=None):
     return z_q, idx, sq, h
 
 
+def pack_partials(sq_sum, hist):
+    return torch.cat([sq_sum.double().reshape(1), hist.double()])
+
+
+def finalize_packed(packed, n_global, D, beta):
+    hist = packed[1:].to(torch.int32)
+    loss, perp = finalize(packed[:1], hist, n_global, D, beta)
+    return loss, perp, hist
+
+
 def keys_to_idx(keys):
     return keys & 0xFFFFFFFF
 
