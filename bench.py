@@ -41,9 +41,9 @@ REF_CUDA_ROWS = 16384       # "same box" bar: the reference's own torch ops on t
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the headline shape, from the `ncu --set full` captures
 # under profiles/ (file named per entry); None = not captured for this build.
 NCU_TRAFFIC = {
-    "search": (4.662e9, "profiles/r01/ncu_full_final_kernels.summary.csv"),
-    "quantize": (2.227e9, "profiles/r01/ncu_full_final_kernels.summary.csv"),
-    "bwd_segmented": (3.267e9, "profiles/r01/ncu_full_final_kernels.summary.csv"),
+    "search": (3.812e9, "profiles/r02/ncu_full_kernels.summary.csv"),         # search_tf32_kernel<2, TOP2>
+    "quantize": (2.345e9, "profiles/r02/ncu_full_kernels.summary.csv"),       # quantize_refine_kernel<2>
+    "bwd_segmented": (3.291e9, "profiles/r02/ncu_full_kernels.summary.csv"),  # segmented_kernel<2, false>
 }
 
 
@@ -416,16 +416,24 @@ def run_kvq(args):
         for _ in range(2):
             step(vq_t)
         torch.cuda.synchronize()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for _ in range(5):
-            step(vq_t)
-        r1.record(); torch.cuda.synchronize()
-        idx_t = last["idx"].reshape(-1)
-        refine = {"ms_per_step_search_tf32": r0.elapsed_time(r1) / 5, "ms_per_step_default": ms_per_step,
+        ab = {"tf32": [], "auto": []}
+        for _rep in range(3):                 # interleaved blocks of 4 steps: both modes see the same thermal / power state
+            for name, module in (("tf32", vq_t), ("auto", vq)):
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record()
+                for _ in range(4):
+                    step(module)
+                r1.record(); torch.cuda.synchronize()
+                ab[name].append(r0.elapsed_time(r1) / 4)
+                if name == "tf32":
+                    idx_t = last["idx"].reshape(-1).clone()
+        t_ms, a_ms = statistics.mean(ab["tf32"]), statistics.mean(ab["auto"])
+        refine = {"ms_per_step_search_tf32": t_ms, "ms_per_step_search_auto": a_ms,
+                  "overhead_of_the_default_mode_pct": 100.0 * (a_ms - t_ms) / t_ms, "blocks_ms": ab,
                   "rows_changed_by_the_exact_pass": int((idx_t != idx_timed).sum()),
-                  "note": "the headline above times the module default (search='auto'); this is the same step with "
-                          "search='tf32' (no top-2 tracking, no exact re-evaluation)"}
+                  "note": "interleaved A/B outside the headline (3 x [4 steps search='tf32', 4 steps search='auto']): "
+                          "'auto' adds top-2 tracking in the search epilogue and the exact float64 re-evaluation fused into "
+                          "the gather kernel; the headline above times 'auto'"}
         del vq_t
 
     # ---- end to end with host buffers (H2D + compute + D2H inside the timed region) --------------------

@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(SEG_WPB * 32, (VPL <= 4) ? 2 : 1) segmented_ke
     const int src_lane = j & 31;
     const int row_c = __shfl_sync(0xffffffffu, cur.x, src_lane);
     const int row_n = __shfl_sync(0xffffffffu, nxt.x, src_lane);
-    if (lane == 0) {
+    if (ring_elect_one()) {
       const int row = ((j >> 5) == consumer_chunk) ? row_c : row_n;
       const uint32_t bar = bars + 8 * js;
       const uint32_t dst = ring_u32 + (uint32_t)js * stage_bytes;

@@ -8,37 +8,51 @@ namespace kvq {
 // ------------------------------------------------------------------------------------------------
 // |E_k|^2, one warp per code (VectorQuantizer.py:60).  4*K*D bytes read, 4*K written.
 // ------------------------------------------------------------------------------------------------
+// One warp per CODES_PER_WARP consecutive codes, all of their loads issued before the first use.
+constexpr int CODES_PER_WARP = 4;
 __global__ void __launch_bounds__(256) code_norms_kernel(const float* __restrict__ E, int64_t K, int D,
                                                          float* __restrict__ e2, int64_t K_pad,
                                                          unsigned* __restrict__ e2max_bits) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (warp >= K_pad) return;
-  if (warp >= K) {
-    if (lane == 0) e2[warp] = INFINITY;  // padded tile columns can never win the argmin
-    return;
+  const int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * CODES_PER_WARP;
+  if (k0 >= K_pad) return;
+  const int nvec = D >> 2;
+  float s[CODES_PER_WARP];
+#pragma unroll
+  for (int c = 0; c < CODES_PER_WARP; ++c) s[c] = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    float4 x[CODES_PER_WARP];
+#pragma unroll
+    for (int c = 0; c < CODES_PER_WARP; ++c)
+      x[c] = (k0 + c < K) ? __ldg(reinterpret_cast<const float4*>(E + (k0 + c) * (int64_t)D) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < CODES_PER_WARP; ++c) {
+      s[c] = fmaf(x[c].x, x[c].x, s[c]); s[c] = fmaf(x[c].y, x[c].y, s[c]);
+      s[c] = fmaf(x[c].z, x[c].z, s[c]); s[c] = fmaf(x[c].w, x[c].w, s[c]);
+    }
   }
-  const float4* row = reinterpret_cast<const float4*>(E + warp * (int64_t)D);
-  float s = 0.f;
-  for (int v = lane; v < (D >> 2); v += 32) {
-    float4 x = __ldg(row + v);
-    s = fmaf(x.x, x.x, s); s = fmaf(x.y, x.y, s); s = fmaf(x.z, x.z, s); s = fmaf(x.w, x.w, s);
-  }
-  s = warp_sum(s);
-  if (lane == 0) {
-    e2[warp] = s;
-    // max_k |E_k|^2 for the tf32 error bound of the exact re-evaluation pass.  s >= 0, so the unsigned order of the
-    // bit patterns is the float order; +inf / NaN patterns sort above every finite value (=> "re-evaluate everything").
-    if (e2max_bits) atomicMax(e2max_bits, __float_as_uint(s));
+#pragma unroll
+  for (int c = 0; c < CODES_PER_WARP; ++c) {
+    const float t = warp_sum(s[c]);
+    if (lane == 0 && k0 + c < K_pad) {
+      if (k0 + c >= K) {
+        e2[k0 + c] = INFINITY;      // padded tile columns can never win the argmin
+      } else {
+        e2[k0 + c] = t;
+        // max_k |E_k|^2 for the tf32 error bound of the exact re-evaluation pass.  t >= 0, so the unsigned order of the
+        // bit patterns is the float order; +inf / NaN patterns sort above every finite value (=> "re-evaluate all").
+        if (e2max_bits) atomicMax(e2max_bits, __float_as_uint(t));
+      }
+    }
   }
 }
 
 int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st, float* e2max) {
   if (K_pad <= 0) return KVQ_OK;
   if (e2max) KVQ_CUDA(cudaMemsetAsync(e2max, 0, sizeof(float), st));
-  const int wpb = 8;
-  int64_t blocks = (K_pad + wpb - 1) / wpb;
-  code_norms_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(E, K, D, e2, K_pad, reinterpret_cast<unsigned*>(e2max));
+  const int per_block = 8 * CODES_PER_WARP;
+  int64_t blocks = (K_pad + per_block - 1) / per_block;
+  code_norms_kernel<<<(unsigned)blocks, 256, 0, st>>>(E, K, D, e2, K_pad, reinterpret_cast<unsigned*>(e2max));
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }
@@ -316,7 +330,7 @@ __global__ void __launch_bounds__(QR_WPB * 32, (VPL <= 4) ? 2 : 1) quantize_refi
     auto issue = [&](int j, int js, int consumer_chunk) {
       const int a_c = __shfl_sync(0xffffffffu, cur_a, j & 31);
       const int a_n = __shfl_sync(0xffffffffu, nxt_a, j & 31);
-      if (lane == 0) {
+      if (ring_elect_one()) {
         const int a = ((j >> 5) == consumer_chunk) ? a_c : a_n;
         const uint32_t bar = bars + 8 * js;
         const uint32_t dst = ring_u32 + (uint32_t)js * stage_bytes;
@@ -495,9 +509,18 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
   __shared__ double part[32];
   const float n_f = (float)n_global;
   double s = 0.0;
-  for (int64_t k = threadIdx.x; k < K; k += blockDim.x) {
-    const float p = (float)hist[k] / n_f;           // mean of a 0/1 column == count / N in fp32
-    s += (double)(p * logf(p + 1e-10f));
+  for (int64_t k0 = threadIdx.x; k0 < K; k0 += 8 * (int64_t)blockDim.x) {
+    int32_t c[8];                                    // eight independent loads in flight per thread
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t k = k0 + u * (int64_t)blockDim.x;
+      c[u] = k < K ? hist[k] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float p = (float)c[u] / n_f;             // mean of a 0/1 column == count / N in fp32
+      s += (double)(p * logf(p + 1e-10f));           // an empty (or out-of-range) slot contributes 0 * log(1e-10) = 0
+    }
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;

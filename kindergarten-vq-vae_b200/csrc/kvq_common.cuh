@@ -108,6 +108,18 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
 // mbarrier per stage; the warp consumes a stage once its barrier phase flips.  No registers are tied up by bytes in
 // flight, so the ring depth -- not the register file -- sets the memory-level parallelism.
 #ifdef __CUDACC__
+// One lane of the (converged) warp.  Issuing the bulk copies under `elect.sync` instead of `if (lane == 0)` lets the
+// compiler keep their operands in uniform registers; under a plain lane test it wraps every UBLKCP in a
+// per-active-thread serialisation loop (~18 instructions each).
+__device__ __forceinline__ bool ring_elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t ring_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ring_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
