@@ -291,14 +291,28 @@ static int forward_partials(const char* who, const float* z, const float* E, int
   KVQ_REQUIRE(ws_bytes >= w.bytes, KVQ_ERR_WORKSPACE, "%s: workspace %zu < %zu bytes", who, ws_bytes, w.bytes);
   if (!sq_sum) sq_sum = w.sq_sum;
   int m; rc = resolve_mode(mode, N, D, K, &m); if (rc) return rc;
-  { ProfScope ps(KVQ_PROF_NORMS, st); rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st, w.e2max); }
-  if (rc) return rc;
-  int deferred = 0;   // tf32_refine: the exact top-2 re-evaluation rides along in the gather kernel
-  rc = run_search(m, z, E, w.e2, w.e2max, N, D, K, idx, w.keys, st, &deferred);
-  if (rc) return rc;
-  KVQ_CUDA(cudaMemsetAsync(sq_sum, 0, sizeof(double), st));
-  KVQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int32_t), st));
+  // fp32 search (explicit, D % 32 != 0, or the default mode on shapes whose tensor-core search would split the code
+  // range -- the reference's own C1 / C2 shapes): four launches for the whole forward.  The norms kernel also clears
+  // the histogram and pre-fills the packed keys, the search MIN-combines into them, the gather kernel reads them and
+  // publishes idx.
+  const bool via_keys = (m == KVQ_SEARCH_FP32) || (m == KVQ_SEARCH_TF32_REFINE && tf32_search_splits(N, K));
+  KVQ_CUDA(cudaMemsetAsync(w.sq_sum, 0, 16, st));                       // sq_sum (8 B) and e2max (4 B) share one block
+  if (sq_sum != w.sq_sum) KVQ_CUDA(cudaMemsetAsync(sq_sum, 0, sizeof(double), st));
   {
+    ProfScope ps(KVQ_PROF_NORMS, st);
+    rc = launch_code_norms(E, K, D, w.e2, pad_codes(K), st, w.e2max, /*e2max_is_zeroed=*/true, hist,
+                           via_keys ? w.keys : nullptr, N);
+  }
+  if (rc) return rc;
+  if (via_keys) {
+    rc = launch_search_fp32(z, E, w.e2, N, D, K, 0, nullptr, w.keys, /*keys_accumulate=*/1, st);
+    if (rc) return rc;
+    ProfScope ps(KVQ_PROF_QUANTIZE, st);
+    rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, sq_sum, hist, st, nullptr, nullptr, nullptr, w.keys);
+  } else {
+    int deferred = 0;   // tf32_refine: the exact top-2 re-evaluation rides along in the gather kernel
+    rc = run_search(m, z, E, w.e2, w.e2max, N, D, K, idx, w.keys, st, &deferred);
+    if (rc) return rc;
     ProfScope ps(KVQ_PROF_QUANTIZE, st);
     rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, sq_sum, hist, st, nullptr,
                          deferred ? reinterpret_cast<const int64_t*>(w.keys) : nullptr, deferred ? w.e2max : nullptr);

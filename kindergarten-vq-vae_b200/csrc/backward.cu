@@ -249,6 +249,84 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const int64
   }
 }
 
+// ---- 2b. the same sort pass for small inputs: ONE block does count, scan and scatter --------------------------------
+// (N <= SMALL_SORT_MAX: the reference's own shapes, where the layer is launch-latency bound.)  1024 threads; warp w owns
+// the contiguous items [w * rounds * 32, (w + 1) * rounds * 32) and visits them in `rounds` rounds of 32, so the ranking
+// is stable exactly as in the tiled kernels.  The first pass also turns the usage histogram into segment offsets
+// (exclusive scan, K <= SMALL_SCAN_MAX), which saves one more launch.
+constexpr int SMALL_SORT_THREADS = 1024;
+constexpr int SMALL_SORT_MAX = 16384;      // items: <= 16 rounds per warp
+constexpr int SMALL_SCAN_MAX = 8192;       // histogram entries scanned inside the first pass
+
+template <bool FIRST>
+__global__ void __launch_bounds__(SMALL_SORT_THREADS) radix_pass_small_kernel(
+    const int64_t* __restrict__ idx, const int2* __restrict__ pairs, int64_t N, const int32_t* __restrict__ n_valid_in,
+    int64_t K, int64_t k_offset, int shift, int2* __restrict__ out, int32_t* __restrict__ n_valid_out,
+    const int32_t* __restrict__ hist, int32_t* __restrict__ offsets, int32_t* __restrict__ hist_total) {
+  extern __shared__ int32_t small_smem[];                 // [32 warps][RADIX] per-warp digit counters
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t digit_base[RADIX];
+  int32_t(*wcnt)[RADIX] = reinterpret_cast<int32_t(*)[RADIX]>(small_smem);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t n = FIRST ? N : (int64_t)*n_valid_in;
+  if (FIRST && hist) {                                    // segment offsets = exclusive scan of the usage histogram
+    int32_t carry = 0;
+    for (int64_t base = 0; base < K; base += SMALL_SORT_THREADS) {
+      const int64_t i = base + threadIdx.x;
+      const int32_t v = (i < K) ? hist[i] : 0;
+      int32_t chunk_total;
+      const int32_t before = block_exclusive_scan_1024(v, warp_tot, &chunk_total);
+      if (i < K) offsets[i] = carry + before;
+      carry += chunk_total;
+    }
+    if (threadIdx.x == 0) *hist_total = carry;
+  }
+  for (int i = threadIdx.x; i < 32 * RADIX; i += SMALL_SORT_THREADS) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  const int rounds = (int)((N + SMALL_SORT_THREADS - 1) / SMALL_SORT_THREADS);      // <= 16
+  const int64_t base = (int64_t)w * rounds * 32;
+  int2 item[16];
+  int32_t where[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    where[r] = -1;
+    if (r < rounds) {
+      item[r] = sort_item<FIRST>(idx, pairs, base + r * 32 + lane, n, K, k_offset);
+      const int digit = item[r].y < 0 ? -1 : ((item[r].y >> shift) & (RADIX - 1));
+      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      int32_t old = 0;
+      if (digit >= 0) old = wcnt[w][digit];
+      __syncwarp();
+      if (digit >= 0 && lane == (__ffs(peers) - 1)) wcnt[w][digit] = old + __popc(peers);
+      __syncwarp();
+      where[r] = digit < 0 ? -1 : (digit | ((old + rank) << RADIX_BITS));
+    }
+  }
+  __syncthreads();
+  // digit totals -> exclusive scan over the 256 digits -> per-warp start positions
+  int32_t total_d = 0;
+  if (threadIdx.x < RADIX)
+    for (int ww = 0; ww < 32; ++ww) total_d += wcnt[ww][threadIdx.x];
+  int32_t all;
+  const int32_t before = block_exclusive_scan_1024(threadIdx.x < RADIX ? total_d : 0, warp_tot, &all);
+  if (threadIdx.x < RADIX) digit_base[threadIdx.x] = before;
+  if (threadIdx.x == 0 && n_valid_out) *n_valid_out = all;
+  __syncthreads();
+  if (threadIdx.x < RADIX) {
+    int32_t run = digit_base[threadIdx.x];
+    for (int ww = 0; ww < 32; ++ww) {
+      const int32_t c = wcnt[ww][threadIdx.x];
+      wcnt[ww][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 16; ++r)
+    if (where[r] >= 0) out[wcnt[w][where[r] & (RADIX - 1)] + (where[r] >> RADIX_BITS)] = item[r];
+}
+
 // ---- 3. segmented pass -----------------------------------------------------------------------------
 // 128-bit reductions into remote memory: one multimem.red into the NVSwitch multicast address (the switch adds the
 // vector into every GPU's replica), or one system-scope red per peer when multicast is not available.
@@ -669,11 +747,28 @@ size_t backward_workspace_bytes(int64_t N, int D, int64_t K) { return carve_back
 // offsets = exclusive_scan(hist); slots = (row, code) stably sorted by code (rows outside [k_offset, k_offset+K) dropped)
 static int build_sorted_slots(const int64_t* idx, const int32_t* hist, int64_t N, int64_t K, int64_t k_offset,
                               const BwdWs& w, cudaStream_t st) {
-  int rc = launch_exclusive_scan(hist, K, w.offsets, w.block_sums, w.totals, st);
-  if (rc) return rc;
   int bits = 0;
   while (((int64_t)1 << bits) < K) ++bits;            // codes are < K
   const int passes = bits <= RADIX_BITS ? 1 : (bits + RADIX_BITS - 1) / RADIX_BITS;
+  if (N <= SMALL_SORT_MAX && K <= SMALL_SCAN_MAX) {
+    // small inputs: one single-block kernel per pass; the first one also scans the histogram
+    const size_t smem = (size_t)32 * RADIX * sizeof(int32_t);
+    for (int pass = 0; pass < passes; ++pass) {
+      int2* dst = ((passes - 1 - pass) % 2 == 0) ? w.slots : w.tmp;
+      const int2* src = (dst == w.slots) ? w.tmp : w.slots;
+      if (pass == 0)
+        radix_pass_small_kernel<true><<<1, SMALL_SORT_THREADS, smem, st>>>(idx, nullptr, N, nullptr, K, k_offset, 0, dst,
+                                                                          w.totals + 1, hist, w.offsets, w.totals);
+      else
+        radix_pass_small_kernel<false><<<1, SMALL_SORT_THREADS, smem, st>>>(nullptr, src, N, w.totals + 1, K, k_offset,
+                                                                           pass * RADIX_BITS, dst, nullptr, nullptr,
+                                                                           nullptr, nullptr);
+      KVQ_LAUNCH_CHECK();
+    }
+    return KVQ_OK;
+  }
+  int rc = launch_exclusive_scan(hist, K, w.offsets, w.block_sums, w.totals, st);
+  if (rc) return rc;
   const int nblk = sort_blocks(N);
   for (int pass = 0; pass < passes; ++pass) {
     const int shift = pass * RADIX_BITS;

@@ -12,25 +12,39 @@ namespace kvq {
 constexpr int CODES_PER_WARP = 4;
 __global__ void __launch_bounds__(256) code_norms_kernel(const float* __restrict__ E, int64_t K, int D,
                                                          float* __restrict__ e2, int64_t K_pad,
-                                                         unsigned* __restrict__ e2max_bits) {
+                                                         unsigned* __restrict__ e2max_bits, int32_t* __restrict__ hist_zero,
+                                                         long long* __restrict__ keys_fill, int64_t n_keys) {
   const int lane = threadIdx.x & 31;
+  // side jobs that would otherwise be launches of their own (they matter when the whole layer takes ~0.1 ms):
+  // clear the usage histogram, pre-fill the packed-key buffer of a split search
+  {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    if (hist_zero) for (int64_t i = tid; i < K; i += nthr) hist_zero[i] = 0;
+    if (keys_fill) for (int64_t i = tid; i < n_keys; i += nthr) keys_fill[i] = KEY_INIT;
+  }
+  __shared__ unsigned block_max[8];
   const int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * CODES_PER_WARP;
-  if (k0 >= K_pad) return;
   const int nvec = D >> 2;
   float s[CODES_PER_WARP];
 #pragma unroll
   for (int c = 0; c < CODES_PER_WARP; ++c) s[c] = 0.f;
-  for (int v = lane; v < nvec; v += 32) {
-    float4 x[CODES_PER_WARP];
+  if (k0 < K) {
+    for (int v = lane; v < nvec; v += 32) {
+      float4 x[CODES_PER_WARP];
 #pragma unroll
-    for (int c = 0; c < CODES_PER_WARP; ++c)
-      x[c] = (k0 + c < K) ? __ldg(reinterpret_cast<const float4*>(E + (k0 + c) * (int64_t)D) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < CODES_PER_WARP; ++c)
+        x[c] = (k0 + c < K) ? __ldg(reinterpret_cast<const float4*>(E + (k0 + c) * (int64_t)D) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < CODES_PER_WARP; ++c) {
-      s[c] = fmaf(x[c].x, x[c].x, s[c]); s[c] = fmaf(x[c].y, x[c].y, s[c]);
-      s[c] = fmaf(x[c].z, x[c].z, s[c]); s[c] = fmaf(x[c].w, x[c].w, s[c]);
+      for (int c = 0; c < CODES_PER_WARP; ++c) {
+        s[c] = fmaf(x[c].x, x[c].x, s[c]); s[c] = fmaf(x[c].y, x[c].y, s[c]);
+        s[c] = fmaf(x[c].z, x[c].z, s[c]); s[c] = fmaf(x[c].w, x[c].w, s[c]);
+      }
     }
   }
+  // max_k |E_k|^2 for the tf32 error bound of the exact re-evaluation pass.  Norms are >= 0, so the unsigned order of the
+  // bit patterns is the float order; +inf / NaN patterns sort above every finite value (=> "re-evaluate everything").
+  // One atomic per block (65536 same-address atomics would cost more than the norms themselves).
+  unsigned wmax = 0;
 #pragma unroll
   for (int c = 0; c < CODES_PER_WARP; ++c) {
     const float t = warp_sum(s[c]);
@@ -39,20 +53,29 @@ __global__ void __launch_bounds__(256) code_norms_kernel(const float* __restrict
         e2[k0 + c] = INFINITY;      // padded tile columns can never win the argmin
       } else {
         e2[k0 + c] = t;
-        // max_k |E_k|^2 for the tf32 error bound of the exact re-evaluation pass.  t >= 0, so the unsigned order of the
-        // bit patterns is the float order; +inf / NaN patterns sort above every finite value (=> "re-evaluate all").
-        if (e2max_bits) atomicMax(e2max_bits, __float_as_uint(t));
+        wmax = max(wmax, __float_as_uint(t));
       }
+    }
+  }
+  if (e2max_bits) {
+    if (lane == 0) block_max[threadIdx.x >> 5] = wmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned m = block_max[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = max(m, block_max[w]);
+      if (m) atomicMax(e2max_bits, m);
     }
   }
 }
 
-int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st, float* e2max) {
+int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st, float* e2max,
+                      bool e2max_is_zeroed, int32_t* hist_zero, long long* keys_fill, int64_t n_keys) {
   if (K_pad <= 0) return KVQ_OK;
-  if (e2max) KVQ_CUDA(cudaMemsetAsync(e2max, 0, sizeof(float), st));
+  if (e2max && !e2max_is_zeroed) KVQ_CUDA(cudaMemsetAsync(e2max, 0, sizeof(float), st));
   const int per_block = 8 * CODES_PER_WARP;
   int64_t blocks = (K_pad + per_block - 1) / per_block;
-  code_norms_kernel<<<(unsigned)blocks, 256, 0, st>>>(E, K, D, e2, K_pad, reinterpret_cast<unsigned*>(e2max));
+  code_norms_kernel<<<(unsigned)blocks, 256, 0, st>>>(E, K, D, e2, K_pad, reinterpret_cast<unsigned*>(e2max), hist_zero,
+                                                     keys_fill, n_keys);
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }
@@ -192,7 +215,8 @@ int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t
 // ------------------------------------------------------------------------------------------------
 template <int VPL>
 __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__ z, const float* __restrict__ E,
-                                                       const int64_t* __restrict__ idx, int64_t N, int D, int64_t K,
+                                                       int64_t* __restrict__ idx, const long long* __restrict__ keys,
+                                                       int64_t N, int D, int64_t K,
                                                        int64_t k_offset, int zero_skipped, float* __restrict__ z_q,
                                                        double* __restrict__ sq_sum, int32_t* __restrict__ hist,
                                                        const ShardPtrs shards) {
@@ -207,7 +231,13 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__
     const int64_t my_row = row0 + lane;
     int64_t code = -1;
     if (my_row < N) {
-      code = idx[my_row] - k_offset;
+      if (keys) {                     // split search: the merged packed keys are the result; publish the index too
+        code = (int64_t)key_index(keys[my_row]);
+        idx[my_row] = code;
+        code -= k_offset;
+      } else {
+        code = idx[my_row] - k_offset;
+      }
       if (code < 0 || code >= K) code = -1;
     }
     // histogram, aggregated over equal codes inside the warp
@@ -471,7 +501,7 @@ static int launch_quantize_refine(const float* z, const float* E, int64_t* idx, 
 
 int launch_quantize(const float* z, const float* E, int64_t* idx, int64_t N, int D, int64_t K,
                     int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st,
-                    const ShardPtrs* shards, const int64_t* idx2, const float* e2max) {
+                    const ShardPtrs* shards, const int64_t* idx2, const float* e2max, const long long* keys) {
   if (N <= 0) return KVQ_OK;
   ShardPtrs sp;
   if (shards) sp = *shards; else { sp.n = 0; sp.k_per = 1; }
@@ -486,7 +516,7 @@ int launch_quantize(const float* z, const float* E, int64_t* idx, int64_t N, int
   const int vpl = (D / 4 + 31) / 32;
 #define KVQ_Q(V)                                                                                            \
   case V:                                                                                                   \
-    quantize_kernel<V><<<blocks, wpb * 32, 0, st>>>(z, E, idx, N, D, K, k_offset, zero_skipped, z_q, sq_sum, hist, sp); \
+    quantize_kernel<V><<<blocks, wpb * 32, 0, st>>>(z, E, idx, keys, N, D, K, k_offset, zero_skipped, z_q, sq_sum, hist, sp); \
     break;
   switch (vpl) {
     KVQ_Q(1) KVQ_Q(2) KVQ_Q(3) KVQ_Q(4) KVQ_Q(5) KVQ_Q(6) KVQ_Q(7) KVQ_Q(8)

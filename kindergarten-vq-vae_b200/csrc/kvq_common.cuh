@@ -178,7 +178,10 @@ struct RemoteGrad {          // batch-sharded backward: where the bucket sums of
 
 // ---- kernels' host launchers (one per translation unit) --------------------------------------------
 // e2max (optional, device scalar): receives max_k |E_k|^2 (for the error bound of the exact top-2 re-evaluation)
-int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st, float* e2max = nullptr);
+// hist_zero / keys_fill (optional): also clear a K-entry histogram / fill an n_keys-entry packed-key buffer with KEY_INIT
+int launch_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, cudaStream_t st, float* e2max = nullptr,
+                      bool e2max_is_zeroed = false, int32_t* hist_zero = nullptr, long long* keys_fill = nullptr,
+                      int64_t n_keys = 0);
 int launch_search_fp32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
                        int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st,
                        const PeerKeys* peers = nullptr);
@@ -205,7 +208,8 @@ int launch_keys_to_idx(const long long* keys, int64_t N, int64_t* idx, cudaStrea
 // idx2 / e2max given: fused exact re-evaluation of the tf32 top-2 pair (idx is then rewritten where the runner-up wins)
 int launch_quantize(const float* z, const float* E, int64_t* idx, int64_t N, int D, int64_t K,
                     int64_t k_offset, int zero_skipped, float* z_q, double* sq_sum, int32_t* hist, cudaStream_t st,
-                    const ShardPtrs* shards = nullptr, const int64_t* idx2 = nullptr, const float* e2max = nullptr);
+                    const ShardPtrs* shards = nullptr, const int64_t* idx2 = nullptr, const float* e2max = nullptr,
+                    const long long* keys = nullptr);   // keys: take the indices from merged packed keys and write idx
 int launch_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, int D, int64_t K, float beta,
                     float* loss, float* perplexity, cudaStream_t st);
 int launch_pack_partials(const double* sq_sum, const int32_t* hist, int64_t K, double* packed, cudaStream_t st);

@@ -201,3 +201,58 @@ def test_tf32_search_returns_idx_together_with_accumulated_keys():
         assert torch.equal(F.keys_to_idx(keys), idx)
         if mode != "auto":
             assert torch.equal(idx, plain)
+
+
+def test_small_shape_step_is_a_handful_of_launches():
+    """The reference's own shapes (BASELINE config 1: N = 4096, D = 768, K = 512) are launch-latency bound: the whole
+    forward is 4 kernels (norms + histogram clear + key fill | search | gather + idx | finalize), the deterministic backward
+    4 (two single-block sort passes, segmented pass, fix-up).  Also prints the eager and CUDA-graph step times."""
+    k = _kvq()
+    from kindergarten_vq_vae_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(64, 64, 768, generator=g).to(DEV).requires_grad_(True)
+    E = torch.randn(512, 768, generator=g)
+    gz = torch.randn(64, 64, 768, generator=g).to(DEV)
+    vq = k.VectorQuantizer(512, 768, 0.25, vq_codebook_init_values=E, min_encodings=False).to(DEV)
+    one = torch.ones((), device=DEV)
+
+    def step():
+        z.grad = None
+        vq.embedding.weight.grad = None
+        loss, z_q, perp, _, idx = vq.forward(z, DEV)
+        torch.autograd.backward([loss, z_q], [one, gz])
+        return idx
+    for _ in range(3):
+        idx = step()
+    torch.cuda.synchronize()
+    n0 = lib.kvq_launch_count()
+    idx = step()
+    torch.cuda.synchronize()
+    launches = lib.kvq_launch_count() - n0
+    assert launches <= 8, launches
+    ref = O.forward_fp32(z.detach().cpu(), E, 0.25)
+    assert O.index_parity(idx.cpu(), ref.idx, z.detach().cpu(), E, exact_fp32=True).unexcused == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    eager_ms = e0.elapsed_time(e1) / 50
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    z.grad = None
+    vq.embedding.weight.grad = None
+    with torch.cuda.graph(graph):
+        step()
+    graph.replay(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(50):
+        graph.replay()
+    e1.record(); torch.cuda.synchronize()
+    print(f"config-1 shape fwd+bwd: {launches} library kernels per step, {eager_ms:.3f} ms eager, "
+          f"{e0.elapsed_time(e1) / 50:.3f} ms as one CUDA graph")
