@@ -118,7 +118,7 @@ int run_search(int mode, const float* z, const float* E, const float* e2, const 
                int64_t* idx, long long* scratch, cudaStream_t st, int* deferred) {
   if (deferred) *deferred = 0;
   if (mode == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, e2, N, D, K, 0, idx, scratch, 0, st);
-  if (mode == KVQ_SEARCH_TF32_REFINE && !tf32_search_splits(N, K)) {
+  if (mode == KVQ_SEARCH_TF32_REFINE && tf32_refine_on_tensor_cores(N, D, K)) {
     // tensor-core search keeping the two best codes per latent, then an exact float64 re-evaluation of the pair
     int64_t* runner_up = reinterpret_cast<int64_t*>(scratch);
     int rc = launch_search_tf32_top2(z, E, e2, N, D, K, idx, runner_up, st);
@@ -126,7 +126,7 @@ int run_search(int mode, const float* z, const float* E, const float* e2, const 
     if (deferred) { *deferred = 1; return KVQ_OK; }   // fused into the gather kernel by the caller
     return launch_refine_top2(z, E, N, D, idx, runner_up, e2max, st);
   }
-  // fp32 mode, and tf32_refine on shapes small enough that the search would be split over CTAs (exact and cheap there)
+  // fp32 mode, and tf32_refine where a few rows face a huge codebook (the split fp32 search is exact and faster there)
   return launch_search_fp32(z, E, e2, N, D, K, 0, idx, scratch, 0, st);
 }
 
@@ -291,11 +291,11 @@ static int forward_partials(const char* who, const float* z, const float* E, int
   KVQ_REQUIRE(ws_bytes >= w.bytes, KVQ_ERR_WORKSPACE, "%s: workspace %zu < %zu bytes", who, ws_bytes, w.bytes);
   if (!sq_sum) sq_sum = w.sq_sum;
   int m; rc = resolve_mode(mode, N, D, K, &m); if (rc) return rc;
-  // fp32 search (explicit, D % 32 != 0, or the default mode on shapes whose tensor-core search would split the code
-  // range -- the reference's own C1 / C2 shapes): four launches for the whole forward.  The norms kernel also clears
+  // fp32 search (explicit, D % 32 != 0, or the default mode when a few rows face a huge codebook): four launches for the
+  // whole forward.  The norms kernel also clears
   // the histogram and pre-fills the packed keys, the search MIN-combines into them, the gather kernel reads them and
   // publishes idx.
-  const bool via_keys = (m == KVQ_SEARCH_FP32) || (m == KVQ_SEARCH_TF32_REFINE && tf32_search_splits(N, K));
+  const bool via_keys = (m == KVQ_SEARCH_FP32) || (m == KVQ_SEARCH_TF32_REFINE && !tf32_refine_on_tensor_cores(N, D, K));
   KVQ_CUDA(cudaMemsetAsync(w.sq_sum, 0, 16, st));                       // sq_sum (8 B) and e2max (4 B) share one block
   if (sq_sum != w.sq_sum) KVQ_CUDA(cudaMemsetAsync(sq_sum, 0, sizeof(double), st));
   {

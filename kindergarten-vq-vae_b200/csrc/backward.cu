@@ -347,8 +347,8 @@ constexpr int SEG_BAR_BYTES = SEG_WPB * SEG_MAX_STAGES * 8;
 // fix-up kernel; `total` is only known on the device)
 __host__ __device__ __forceinline__ int seg_slots_per_warp(int total, int n_warps) {
   const int per = (total + n_warps - 1) / n_warps;
-  const int r = (per + 31) & ~31;
-  return r < 32 ? 32 : r;
+  const int r = per >= 32 ? ((per + 31) & ~31) : ((per + 7) & ~7);   // small inputs: granules of 8 slots, more warps
+  return r < 8 ? 8 : r;
 }
 
 struct SegPartials {
@@ -718,7 +718,7 @@ struct BwdWs {
 };
 static inline int sort_blocks(int64_t N) { return (int)((N + SORT_TILE - 1) / SORT_TILE); }
 static inline int seg_warps_cap(int64_t N) {
-  const int64_t w = (N + 31) / 32;
+  const int64_t w = (N + 7) / 8;
   return (int)min_i64(SEG_WARPS_CAP, w > 0 ? w : 1);
 }
 
@@ -818,7 +818,7 @@ static int launch_segmented(const float* z, const float* E, const float* g_zq, c
   int stages, bps;
   size_t smem;
   seg_geometry(D, has_g, vpl, &stages, &bps, &smem);
-  int n_warps = (int)min_i64((N + 31) / 32, (int64_t)sm_count() * bps * SEG_WPB);
+  int n_warps = (int)min_i64((N + 7) / 8, (int64_t)sm_count() * bps * SEG_WPB);
   if (n_warps > seg_warps_cap(N)) n_warps = seg_warps_cap(N);
   const unsigned blocks = (unsigned)((n_warps + SEG_WPB - 1) / SEG_WPB);
   SegPartials part{w.part_sums, w.part_codes};

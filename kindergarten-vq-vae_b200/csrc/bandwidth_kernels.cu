@@ -474,10 +474,13 @@ static int launch_quantize_refine(const float* z, const float* E, int64_t* idx, 
     bps = 1;
   }
   const size_t smem = QR_BAR_BYTES + (size_t)stages * sb;
+  // a warp takes at least 8 rows (small inputs spread over more warps), a multiple of 32 once there is enough work
   const int64_t max_warps = (int64_t)sm_count() * bps * QR_WPB;
-  const int64_t chunks = (N + 31) / 32;
-  const int64_t n_warps = chunks < max_warps ? chunks : max_warps;
-  const int rows_per_warp = (int)(((N + n_warps - 1) / n_warps + 31) / 32 * 32);
+  const int64_t want = (N + 7) / 8;
+  const int64_t n_warps0 = want < max_warps ? want : max_warps;
+  int rows_per_warp = (int)((N + n_warps0 - 1) / n_warps0);
+  rows_per_warp = rows_per_warp >= 32 ? (rows_per_warp + 31) / 32 * 32 : (rows_per_warp + 7) / 8 * 8;
+  const int64_t n_warps = (N + rows_per_warp - 1) / rows_per_warp;
   const unsigned blocks = (unsigned)((n_warps + QR_WPB - 1) / QR_WPB);
   const float c2 = refine_bound_c2();
   KVQ_REQUIRE((((uintptr_t)z | (uintptr_t)E | (uintptr_t)z_q) & 15) == 0, KVQ_ERR_ARG,

@@ -742,7 +742,8 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   const int64_t m_groups = (m_tiles + CG - 1) / CG;
   const int groups = sm_count() / CG;                      // concurrently resident CTA groups
   int ksplit = 1;
-  if (m_groups < groups) ksplit = (int)min_i64(p.n_tiles, (groups + m_groups - 1) / m_groups);
+  // (the top-2 epilogue keeps per-row state across the whole code range: never split it)
+  if (m_groups < groups && EPI != EPI_TOP2) ksplit = (int)min_i64(p.n_tiles, (groups + m_groups - 1) / m_groups);
   p.tiles_per_split = (p.n_tiles + ksplit - 1) / ksplit;
   p.ksplit = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.n_items = m_groups * p.ksplit;
@@ -888,10 +889,21 @@ int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t 
   return t5::launch_cg<2, t5::EPI_ARGMIN>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers, nullptr);
 }
 
-// Would the tensor-core search split the code range over CTAs for this shape?  (Then the top-2 variant is not used.)
-bool tf32_search_splits(int64_t N, int64_t K) {
+// Does the default mode (tensor-core top-2 search + exact re-evaluation) run on the tensor cores for this shape?
+// The top-2 epilogue cannot merge runner-ups across CTAs, so it always sweeps the whole code range per row group
+// (no code-range split).  With few row groups that leaves SMs idle -- yet it still beats the CUDA-core fp32 search by a
+// wide margin on the reference's own shapes (config 1: ~13 us against ~110 us).  Only when a handful of rows face a huge
+// codebook does the split fp32 search win; the estimate below compares the two (MMA issue time of one CTA pair's sweep
+// against fp32 FMA throughput of the whole GPU).
+bool tf32_refine_on_tensor_cores(int64_t N, int D, int64_t K) {
   const int64_t m_groups = ((N + t5::BLOCK_M - 1) / t5::BLOCK_M + 1) / 2;
-  return m_groups < sm_count() / 2 && K > t5::BLOCK_N;
+  const int groups = sm_count() / 2;
+  if (m_groups >= groups || K <= t5::BLOCK_N) return true;
+  const double waves = (double)((m_groups + groups - 1) / groups);
+  const double n_tiles = (double)((K + t5::BLOCK_N - 1) / t5::BLOCK_N);
+  const double t_tensor = waves * n_tiles * (double)(D / t5::BLOCK_K) * 0.30e-6;   // 4 MMAs x 128 cycles per k-block
+  const double t_fp32 = 2.0 * (double)N * (double)K * (double)D / 30e12;           // measured 30-39 TFLOP/s
+  return t_tensor < t_fp32;
 }
 
 int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
