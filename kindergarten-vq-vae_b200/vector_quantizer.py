@@ -95,6 +95,37 @@ def _vq_backward(ctx, g_loss, g_zq, g_perp, g_idx, g_hist):
 _vq_forward_op.register_autograd(_vq_backward, setup_context=_vq_setup_context)
 
 
+class _VQFunction(torch.autograd.Function):
+    """The same forward / backward as the dispatcher operators above, as a plain autograd.Function: used in eager mode,
+    where the operator dispatch costs ~0.1 ms per step -- as much as the whole layer at the reference's own shapes."""
+
+    @staticmethod
+    def forward(ctx, z: Tensor, E: Tensor, beta: float, mode: str):
+        loss, z_q, perplexity, idx, hist = F.vq_forward(z, E, beta, mode=mode)
+        loss, perplexity = loss.clone(), perplexity.clone()    # fresh 0-d tensors (in-place scaling, Trainer.py:104)
+        ctx.save_for_backward(z, E, idx, hist)
+        ctx.beta = beta
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(perplexity, idx, hist)
+        return loss, z_q, perplexity, idx, hist
+
+    @staticmethod
+    def backward(ctx, g_loss, g_zq, g_perp, g_idx, g_hist):
+        z, E, idx, hist = ctx.saved_tensors
+        need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_loss is None and g_zq is None:
+            return None, None, None, None
+        if g_loss is None:
+            return (g_zq if need_dz else None), (torch.zeros_like(E) if need_dE else None), None, None
+        if g_zq is not None:
+            g_zq = g_zq.contiguous()
+            if g_zq.dtype != torch.float32:
+                g_zq = g_zq.float()
+        g_loss = g_loss.detach().to(torch.float32).contiguous()
+        dz, dE = F.vq_backward(z, E, idx, hist, ctx.beta, g_zq=g_zq, g_loss=g_loss, need_dz=need_dz, need_dE=need_dE)
+        return dz, dE, None, None
+
+
 class VectorQuantizer(nn.Module):
     """
     Discretization bottleneck part of the VQ-VAE (B200-native).
@@ -147,13 +178,16 @@ class VectorQuantizer(nn.Module):
             raise RuntimeError("VectorQuantizer (kvq) runs on CUDA only: there is no CPU fallback "
                                f"(z on {z.device}, codebook on {weight.device})")
         N = z_flattened.shape[0]
-        loss, z_q, perplexity, idx, _hist = _vq_forward_op(z_flattened, weight, float(self.beta), self.search)
+        if torch.compiler.is_compiling():      # traced (model.compile(), main.py:83): one opaque dispatcher node
+            loss, z_q, perplexity, idx, _hist = _vq_forward_op(z_flattened, weight, float(self.beta), self.search)
+        else:                                  # eager: same C-ABI calls without the operator-dispatch overhead
+            loss, z_q, perplexity, idx, _hist = _VQFunction.apply(z_flattened, weight, float(self.beta), self.search)
         z_q = z_q.view(z.shape)
 
         want = self.return_min_encodings
         if want == "auto":
             want = N * self.n_e * 4 <= ONEHOT_AUTO_BYTES
-        min_encodings = _onehot_op(idx, self.n_e) if want else None    # VectorQuantizer.py:67-68
+        min_encodings = (_onehot_op(idx, self.n_e) if torch.compiler.is_compiling() else F.onehot(idx, self.n_e)) if want else None    # VectorQuantizer.py:67-68
 
         min_encoding_indices = idx.reshape((batch_size, seq_len, 1))  # VectorQuantizer.py:90
         return loss, z_q, perplexity, min_encodings, min_encoding_indices

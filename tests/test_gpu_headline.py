@@ -256,3 +256,25 @@ def test_small_shape_step_is_a_handful_of_launches():
     e1.record(); torch.cuda.synchronize()
     print(f"config-1 shape fwd+bwd: {launches} library kernels per step, {eager_ms:.3f} ms eager, "
           f"{e0.elapsed_time(e1) / 50:.3f} ms as one CUDA graph")
+
+
+def test_dz_only_backward_passes_the_upstream_gradient_through_for_foreign_codes():
+    """kvq_backward on a code shard, dz only: latents whose code another shard owns get dz = g_zq (not garbage)."""
+    F = _kvq().functional
+    g = torch.Generator().manual_seed(2)
+    N, D, K = 500, 64, 100
+    z = torch.randn(N, D, generator=g).to(DEV)
+    E = torch.randn(K, D, generator=g).to(DEV)
+    gz = torch.randn(N, D, generator=g).to(DEV)
+    idx = torch.randint(0, K, (N,), generator=g).to(DEV)
+    gl = torch.tensor(2.0, device=DEV)
+    lo, hi = 30, 70                                            # this "rank" owns codes [30, 70)
+    dz, _ = F.vq_backward(z, E[lo:hi].contiguous(), idx, None, 0.25, g_zq=gz, g_loss=gl, need_dz=True, need_dE=False,
+                          k_offset=lo, n_global=N)
+    mine = (idx >= lo) & (idx < hi)
+    c1 = 2.0 * 2.0 / (N * D)
+    assert torch.equal(dz[~mine], gz[~mine])
+    assert torch.allclose(dz[mine], gz[mine] + c1 * (z[mine] - E[idx[mine]]), rtol=1e-5, atol=1e-7)
+    with pytest.raises(RuntimeError, match="separate calls"):
+        F.vq_backward(z, E[lo:hi].contiguous(), idx, torch.zeros(hi - lo, dtype=torch.int32, device=DEV), 0.25, g_zq=gz,
+                      g_loss=gl, need_dz=True, need_dE=True, k_offset=lo)
