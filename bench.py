@@ -41,9 +41,9 @@ REF_CUDA_ROWS = 16384       # "same box" bar: the reference's own torch ops on t
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the headline shape, from the `ncu --set full` captures
 # under profiles/ (file named per entry); None = not captured for this build.
 NCU_TRAFFIC = {
-    "search": (3.812e9, "profiles/r02/ncu_full_kernels.summary.csv"),         # search_tf32_kernel<2, TOP2>
-    "quantize": (2.345e9, "profiles/r02/ncu_full_kernels.summary.csv"),       # quantize_refine_kernel<2>
-    "bwd_segmented": (3.291e9, "profiles/r02/ncu_full_kernels.summary.csv"),  # segmented_kernel<2, false>
+    "search": (3.912e9, "profiles/r02/ncu_full_kernels.summary.csv"),         # search_tf32_kernel<2, TOP2>
+    "quantize": (2.343e9, "profiles/r02/ncu_full_kernels.summary.csv"),       # quantize_refine_kernel<2>
+    "bwd_segmented": (3.290e9, "profiles/r02/ncu_full_kernels.summary.csv"),  # segmented_kernel<2, false>
 }
 
 

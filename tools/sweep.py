@@ -67,7 +67,7 @@ def single():
             z, gz, E = make(dev, N, D, K, init)
             z3 = z.view(B, S, D).requires_grad_(True)
             g3 = gz.view(B, S, D)
-            vq = kvq.VectorQuantizer(K, D, BETA, vq_codebook_init_values=E, search="tf32", min_encodings=False).to(dev)
+            vq = kvq.VectorQuantizer(K, D, BETA, vq_codebook_init_values=E, min_encodings=False).to(dev)   # default search mode
             one = torch.ones((), device=dev)
 
             def step():
@@ -76,7 +76,7 @@ def single():
                 torch.autograd.backward([loss, z_q], [one, g3])
             ms = timed(step, iters=10 if N >= (1 << 18) else 50)
             prof = profile(lib, step)
-            out = dict(config=name, N=N, D=D, K=K, init=init, ms_fwd_bwd=ms, latents_per_s=N / ms * 1e3, kernel_ms=prof)
+            out = dict(config=name, N=N, D=D, K=K, init=init, search=vq.search, ms_fwd_bwd=ms, latents_per_s=N / ms * 1e3, kernel_ms=prof)
             if prof["search"]:
                 out["search_tflops"] = 2.0 * N * K * D / prof["search"] / 1e9
             if N <= 32768:   # small shapes are launch-bound: the same step as ONE CUDA-graph launch
@@ -113,7 +113,7 @@ def multi():
         z = torch.randn(N, D, device=dev, generator=g); gz = torch.randn(N, D, device=dev, generator=g)
         per = (K + world - 1) // world
         ge = torch.Generator(device=dev).manual_seed(1000 + rank)       # this rank's codebook rows
-        vq = kvq.CodebookShardedVectorQuantizer(K, D, BETA, search="tf32", exchange=exchange).to(dev)
+        vq = kvq.CodebookShardedVectorQuantizer(K, D, BETA, exchange=exchange).to(dev)
         with torch.no_grad():
             vq.embedding.weight.copy_(torch.randn(per, D, device=dev, generator=ge))
         z3 = z.view(N // 64, 64, D).requires_grad_(True); g3 = gz.view_as(z3)
@@ -141,7 +141,7 @@ def multi():
         z = torch.randn(n_local, D, device=dev, generator=g); gz = torch.randn(n_local, D, device=dev, generator=g)
         ge = torch.Generator(device=dev).manual_seed(7)
         E = torch.randn(K, D, device=dev, generator=ge)
-        vq = kvq.BatchShardedVectorQuantizer(K, D, BETA, vq_codebook_init_values=E, search="tf32", exchange=exchange).to(dev)
+        vq = kvq.BatchShardedVectorQuantizer(K, D, BETA, vq_codebook_init_values=E, exchange=exchange).to(dev)
         z3 = z.view(n_local // 64, 64, D).requires_grad_(True); g3 = gz.view_as(z3)
 
         def step():
