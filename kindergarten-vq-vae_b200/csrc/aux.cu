@@ -180,6 +180,11 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
     const int64_t wave = (int64_t)(sm_count() / 2) * 256;
     bounds.push_back(0);
     if (wave >= 128 && rows_per_chunk > wave && N >= 2 * wave + rows_per_chunk) {
+      // lead-in: the return direction moves as many bytes as the inbound one and cannot start before the first chunk has
+      // been searched, so the very first chunk is kept small (one sweep over the codebook takes the same time for any
+      // row count up to a full wave); then a one-wave chunk, then the coarse middle, then a one-wave tail
+      const int64_t lead = 4096;
+      if (lead < wave) bounds.push_back(lead);
       bounds.push_back(wave);
       while (bounds.back() + rows_per_chunk < N - wave) bounds.push_back(bounds.back() + rows_per_chunk);
       if (bounds.back() < N - wave) bounds.push_back(N - wave);
@@ -212,11 +217,13 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   int32_t* hist = sharded ? hist_dev : hp.hist;
   float* dE = sharded ? dE_dev : hp.dE;
 
-  cudaEvent_t* ev_in = new cudaEvent_t[chunks];
+  cudaEvent_t* ev_in = new cudaEvent_t[chunks];     // z chunk has landed (the search may start)
+  cudaEvent_t* ev_g = new cudaEvent_t[chunks];      // upstream-gradient chunk has landed (needed by dz only)
   cudaEvent_t* ev_done = new cudaEvent_t[chunks];
   cudaEvent_t ev_E, ev_final;
   for (int64_t c = 0; c < chunks; ++c) {
     cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_g[c], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&ev_E, cudaEventDisableTiming);
@@ -240,8 +247,9 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   for (int64_t c = 0; c < chunks && status == KVQ_OK; ++c) {
     const int64_t r0 = bounds[c], rows = bounds[c + 1] - bounds[c];
     KVQ_TRYC(cudaMemcpyAsync(hp.z + r0 * D, z_h + r0 * D, (size_t)rows * D * 4, cudaMemcpyHostToDevice, hp.s_in));
-    KVQ_TRYC(cudaMemcpyAsync(hp.g + r0 * D, g_h + r0 * D, (size_t)rows * D * 4, cudaMemcpyHostToDevice, hp.s_in));
     KVQ_TRYC(cudaEventRecord(ev_in[c], hp.s_in));
+    KVQ_TRYC(cudaMemcpyAsync(hp.g + r0 * D, g_h + r0 * D, (size_t)rows * D * 4, cudaMemcpyHostToDevice, hp.s_in));
+    KVQ_TRYC(cudaEventRecord(ev_g[c], hp.s_in));
   }
   // compute
   KVQ_TRYC(cudaStreamWaitEvent(hp.s_cmp, ev_E, 0));
@@ -258,6 +266,7 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
                             deferred ? e2max : nullptr));
     // dz depends only on this chunk's rows and the (host-given) loss weight: compute it now so that its
     // device->host copy overlaps the search of the next chunk.
+    KVQ_TRYC(cudaStreamWaitEvent(hp.s_cmp, ev_g[c], 0));
     KVQ_TRY(launch_backward(hp.z + r0 * D, hp.E, hp.idx + r0, nullptr, hp.g + r0 * D, hp.scal + 2, rows, D, K, 0, beta,
                             n_global, hp.dz + r0 * D, nullptr, nullptr, 0, hp.s_cmp));
     KVQ_TRYC(cudaEventRecord(ev_done[c], hp.s_cmp));
@@ -284,9 +293,9 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   KVQ_TRYC(cudaStreamSynchronize(hp.s_out));
 #undef KVQ_TRY
 #undef KVQ_TRYC
-  for (int64_t c = 0; c < chunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_done[c]); }
+  for (int64_t c = 0; c < chunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_g[c]); cudaEventDestroy(ev_done[c]); }
   cudaEventDestroy(ev_E); cudaEventDestroy(ev_final);
-  delete[] ev_in; delete[] ev_done;
+  delete[] ev_in; delete[] ev_g; delete[] ev_done;
   return status;
 }
 
