@@ -188,6 +188,7 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
       bounds.push_back(wave);
       while (bounds.back() + rows_per_chunk < N - wave) bounds.push_back(bounds.back() + rows_per_chunk);
       if (bounds.back() < N - wave) bounds.push_back(N - wave);
+      if (lead < wave) bounds.push_back(N - lead);      // lead-out: little left to search and return after the last upload
       bounds.push_back(N);
     } else {
       while (bounds.back() + rows_per_chunk < N) bounds.push_back(bounds.back() + rows_per_chunk);
