@@ -33,9 +33,33 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_WS_BYTES = {}
+
+
 def workspace(N: int, D: int, K: int, device) -> torch.Tensor:
-    nbytes = _lib.load().kvq_workspace_bytes(N, D, K)
+    key = (N, D, K)
+    nbytes = _WS_BYTES.get(key)
+    if nbytes is None:
+        nbytes = _WS_BYTES[key] = _lib.load().kvq_workspace_bytes(N, D, K)
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+class _on_device:
+    """`with _on_device(d)` only when d is not already current (the context manager costs ~10 us per use, which
+    matters when the whole layer takes 0.1 ms at the reference's shapes)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def device_info() -> Tuple[int, int, int]:
@@ -51,7 +75,7 @@ def code_norms(E: torch.Tensor, K_pad: Optional[int] = None) -> torch.Tensor:
     K, D = E.shape
     K_pad = K if K_pad is None else K_pad
     out = torch.empty(K_pad, dtype=torch.float32, device=E.device)
-    with torch.cuda.device(E.device):
+    with _on_device(E.device):
         check(_lib.load().kvq_code_norms(E.data_ptr(), K, D, out.data_ptr(), K_pad, _stream()), "kvq_code_norms")
     return out
 
@@ -75,7 +99,7 @@ def search(z: torch.Tensor, E: torch.Tensor, *, mode: str = "auto", k_offset: in
         _req(keys, "keys", torch.int64)
     if ws is None:
         ws = workspace(N, D, K, z.device)
-    with torch.cuda.device(z.device):
+    with _on_device(z.device):
         check(_lib.load().kvq_search(z.data_ptr(), E.data_ptr(), N, D, K, k_offset, SEARCH_MODES[mode], _ptr(idx),
                                      _ptr(keys), int(bool(keys_accumulate)), ws.data_ptr(), ws.numel(), _stream()),
               "kvq_search")
@@ -85,7 +109,7 @@ def search(z: torch.Tensor, E: torch.Tensor, *, mode: str = "auto", k_offset: in
 def keys_to_idx(keys: torch.Tensor) -> torch.Tensor:
     _req(keys, "keys", torch.int64)
     idx = torch.empty_like(keys)
-    with torch.cuda.device(keys.device):
+    with _on_device(keys.device):
         check(_lib.load().kvq_keys_to_idx(keys.data_ptr(), keys.numel(), idx.data_ptr(), _stream()), "kvq_keys_to_idx")
     return idx
 
@@ -101,7 +125,7 @@ def quantize(z: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, *, k_offset: i
         sq_sum = torch.zeros(1, dtype=torch.float64, device=z.device)
     if hist is None:
         hist = torch.zeros(K, dtype=torch.int32, device=z.device)
-    with torch.cuda.device(z.device):
+    with _on_device(z.device):
         check(_lib.load().kvq_quantize(z.data_ptr(), E.data_ptr(), idx.data_ptr(), N, D, K, k_offset,
                                        int(zero_skipped), z_q.data_ptr(), sq_sum.data_ptr(), hist.data_ptr(),
                                        _stream()), "kvq_quantize")
@@ -110,11 +134,12 @@ def quantize(z: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, *, k_offset: i
 
 def finalize(sq_sum: torch.Tensor, hist: torch.Tensor, n_global: int, D: int, beta: float):
     _req(sq_sum, "sq_sum", torch.float64); _req(hist, "hist", torch.int32)
-    out = torch.empty(2, dtype=torch.float32, device=hist.device)
-    with torch.cuda.device(hist.device):
+    loss = torch.empty((), dtype=torch.float32, device=hist.device)      # fresh 0-d tensors, not views: the training loop
+    perp = torch.empty((), dtype=torch.float32, device=hist.device)      # scales the loss in place (Trainer.py:104)
+    with _on_device(hist.device):
         check(_lib.load().kvq_finalize(sq_sum.data_ptr(), hist.data_ptr(), n_global, D, hist.numel(), beta,
-                                       out.data_ptr(), out.data_ptr() + 4, _stream()), "kvq_finalize")
-    return out[0], out[1]
+                                       loss.data_ptr(), perp.data_ptr(), _stream()), "kvq_finalize")
+    return loss, perp
 
 
 def vq_forward(z: torch.Tensor, E: torch.Tensor, beta: float, *, mode: str = "auto",
@@ -127,15 +152,16 @@ def vq_forward(z: torch.Tensor, E: torch.Tensor, beta: float, *, mode: str = "au
         raise RuntimeError(f"z has {D} features but the codebook has {E.shape[1]}")
     z_q = torch.empty_like(z)
     idx = torch.empty(N, dtype=torch.int64, device=z.device)
-    scal = torch.empty(2, dtype=torch.float32, device=z.device)
+    loss = torch.empty((), dtype=torch.float32, device=z.device)         # fresh 0-d tensors, not views of one buffer: the
+    perp = torch.empty((), dtype=torch.float32, device=z.device)         # training loop scales the loss in place (Trainer.py:104)
     hist = torch.empty(K, dtype=torch.int32, device=z.device)
     if ws is None:
         ws = workspace(N, D, K, z.device)
-    with torch.cuda.device(z.device):
+    with _on_device(z.device):
         check(_lib.load().kvq_forward(z.data_ptr(), E.data_ptr(), N, D, K, float(beta), SEARCH_MODES[mode],
-                                      z_q.data_ptr(), idx.data_ptr(), scal.data_ptr(), scal.data_ptr() + 4,
+                                      z_q.data_ptr(), idx.data_ptr(), loss.data_ptr(), perp.data_ptr(),
                                       hist.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "kvq_forward")
-    return scal[0], z_q, scal[1], idx, hist
+    return loss, z_q, perp, idx, hist
 
 
 def vq_forward_partials(z: torch.Tensor, E: torch.Tensor, *, mode: str = "auto", ws: Optional[torch.Tensor] = None):
@@ -152,7 +178,7 @@ def vq_forward_partials(z: torch.Tensor, E: torch.Tensor, *, mode: str = "auto",
     hist = torch.empty(K, dtype=torch.int32, device=z.device)
     if ws is None:
         ws = workspace(N, D, K, z.device)
-    with torch.cuda.device(z.device):
+    with _on_device(z.device):
         check(_lib.load().kvq_forward_partials(z.data_ptr(), E.data_ptr(), N, D, K, SEARCH_MODES[mode], z_q.data_ptr(),
                                                idx.data_ptr(), sq_sum.data_ptr(), hist.data_ptr(), ws.data_ptr(),
                                                ws.numel(), _stream()), "kvq_forward_partials")
@@ -164,7 +190,7 @@ def pack_partials(sq_sum: torch.Tensor, hist: torch.Tensor) -> torch.Tensor:
     _req(sq_sum, "sq_sum", torch.float64); _req(hist, "hist", torch.int32)
     K = hist.numel()
     packed = torch.empty(K + 1, dtype=torch.float64, device=hist.device)
-    with torch.cuda.device(hist.device):
+    with _on_device(hist.device):
         check(_lib.load().kvq_pack_partials(sq_sum.data_ptr(), hist.data_ptr(), K, packed.data_ptr(), _stream()),
               "kvq_pack_partials")
     return packed
@@ -174,12 +200,13 @@ def finalize_packed(packed: torch.Tensor, n_global: int, D: int, beta: float):
     """loss, perplexity and the global usage histogram from the all-reduced buffer of `pack_partials`."""
     _req(packed, "packed", torch.float64)
     K = packed.numel() - 1
-    out = torch.empty(2, dtype=torch.float32, device=packed.device)
+    loss = torch.empty((), dtype=torch.float32, device=packed.device)
+    perp = torch.empty((), dtype=torch.float32, device=packed.device)
     hist = torch.empty(K, dtype=torch.int32, device=packed.device)
-    with torch.cuda.device(packed.device):
-        check(_lib.load().kvq_finalize_packed(packed.data_ptr(), n_global, D, K, beta, out.data_ptr(), out.data_ptr() + 4,
+    with _on_device(packed.device):
+        check(_lib.load().kvq_finalize_packed(packed.data_ptr(), n_global, D, K, beta, loss.data_ptr(), perp.data_ptr(),
                                               hist.data_ptr(), _stream()), "kvq_finalize_packed")
-    return out[0], out[1], hist
+    return loss, perp, hist
 
 
 def vq_backward(z: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, hist: Optional[torch.Tensor], beta: float, *,
@@ -207,7 +234,7 @@ def vq_backward(z: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, hist: Optio
         _req(hist, "hist", torch.int32)
         if ws is None:
             ws = workspace(N, D, K, z.device)
-    with torch.cuda.device(z.device):
+    with _on_device(z.device):
         check(_lib.load().kvq_backward(z.data_ptr(), E.data_ptr(), idx.data_ptr(), _ptr(hist), _ptr(g_zq),
                                        _ptr(g_loss), N, D, K, k_offset, float(beta),
                                        N if n_global is None else n_global, _ptr(dz), _ptr(dE), _ptr(ws),
@@ -225,7 +252,7 @@ def dz_from_zq(z: torch.Tensor, z_q: torch.Tensor, g_zq: Optional[torch.Tensor],
         _req(g_loss, "g_loss", torch.float32)
     N, D = z.shape
     dz = torch.empty_like(z)
-    with torch.cuda.device(z.device):
+    with _on_device(z.device):
         check(_lib.load().kvq_dz_from_zq(z.data_ptr(), z_q.data_ptr(), _ptr(g_zq), _ptr(g_loss), N, D, n_global,
                                          dz.data_ptr(), _stream()), "kvq_dz_from_zq")
     return dz
@@ -236,7 +263,7 @@ def onehot(idx: torch.Tensor, K: int) -> torch.Tensor:
     _req(idx, "idx", torch.int64)
     N = idx.numel()
     out = torch.empty(N, K, dtype=torch.float32, device=idx.device)
-    with torch.cuda.device(idx.device):
+    with _on_device(idx.device):
         check(_lib.load().kvq_onehot(idx.data_ptr(), N, K, out.data_ptr(), _stream()), "kvq_onehot")
     return out
 
@@ -308,7 +335,7 @@ def search_peers(z: torch.Tensor, E: torch.Tensor, peer_key_ptrs, my_rank: int, 
     if ws is None:
         ws = workspace(N, D, K, z.device)
     arr = (ctypes.c_void_p * len(peer_key_ptrs))(*[int(p) for p in peer_key_ptrs])
-    with torch.cuda.device(z.device):
+    with _on_device(z.device):
         check(_lib.load().kvq_search_peers(z.data_ptr(), E.data_ptr(), N, D, K, k_offset, SEARCH_MODES[mode], arr,
                                            len(peer_key_ptrs), my_rank, ws.data_ptr(), ws.numel(), _stream()),
               "kvq_search_peers")
@@ -323,7 +350,7 @@ def quantize_shards(z: torch.Tensor, shard_ptrs, k_per: int, idx: torch.Tensor, 
     sq_sum = torch.zeros(1, dtype=torch.float64, device=z.device)
     hist = torch.zeros(K_total, dtype=torch.int32, device=z.device)
     arr = (ctypes.c_void_p * len(shard_ptrs))(*[int(p) for p in shard_ptrs])
-    with torch.cuda.device(z.device):
+    with _on_device(z.device):
         check(_lib.load().kvq_quantize_shards(z.data_ptr(), arr, len(shard_ptrs), k_per, idx.data_ptr(), N, D, K_total,
                                               z_q.data_ptr(), sq_sum.data_ptr(), hist.data_ptr(), _stream()),
               "kvq_quantize_shards")
@@ -346,7 +373,7 @@ def vq_backward_peers(z: torch.Tensor, E: torch.Tensor, idx: torch.Tensor, hist:
     if ws is None:
         ws = workspace(N, D, K, z.device)
     arr = (ctypes.c_void_p * len(dE_peer_ptrs))(*[int(p) for p in dE_peer_ptrs])
-    with torch.cuda.device(z.device):
+    with _on_device(z.device):
         check(_lib.load().kvq_backward_peers(z.data_ptr(), E.data_ptr(), idx.data_ptr(), hist.data_ptr(), _ptr(g_zq),
                                              g_loss.data_ptr(), N, D, K, float(beta), n_global, _ptr(dz),
                                              int(dE_multicast_ptr) if dE_multicast_ptr else None, arr, len(dE_peer_ptrs),

@@ -76,7 +76,6 @@ class _BatchShardedFn(torch.autograd.Function):
         if _world(group) > 1:
             dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
         loss, perplexity, hist = F.finalize_packed(packed, n_global, D, beta)
-        loss, perplexity = loss.clone(), perplexity.clone()
         ctx.save_for_backward(z, E, idx, hist_local)
         ctx.beta, ctx.group, ctx.n_global, ctx.grad_peer = beta, group, n_global, grad_peer
         ctx.set_materialize_grads(False)
@@ -182,7 +181,6 @@ class _CodebookShardedFn(torch.autograd.Function):
         else:
             hist = hist_local
         loss, perplexity = F.finalize(sq_sum, hist, N, D, beta)
-        loss, perplexity = loss.clone(), perplexity.clone()
         ctx.save_for_backward(z, E_param, idx, hist_local, z_q)
         ctx.beta, ctx.k_offset, ctx.k_valid = beta, k_offset, k_valid
         ctx.set_materialize_grads(False)
@@ -260,7 +258,6 @@ class _CodebookShardedFusedFn(torch.autograd.Function):
         kh.barrier(channel=0)                       # peers are done reading this rank's mirror
         hist = hist_all[:k_total].contiguous()
         loss, perplexity = F.finalize(sq_sum, hist, N, D, beta)
-        loss, perplexity = loss.clone(), perplexity.clone()
         hist_local = hist_all[k_offset:k_offset + k_valid].contiguous()
         ctx.save_for_backward(z, E_param, idx, hist_local, z_q)
         ctx.beta, ctx.k_offset, ctx.k_valid = beta, k_offset, k_valid

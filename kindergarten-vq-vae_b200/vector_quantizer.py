@@ -30,10 +30,9 @@ ONEHOT_AUTO_BYTES = 64 << 20
 
 @torch.library.custom_op("kvq::vq_forward", mutates_args=())
 def _vq_forward_op(z: Tensor, E: Tensor, beta: float, mode: str) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    loss, z_q, perplexity, idx, hist = F.vq_forward(z, E, beta, mode=mode)
-    # fresh 0-d tensors (not views of the 2-float result buffer): the training loop multiplies the loss in place
+    # loss and perplexity come back as fresh 0-d tensors (not views): the training loop multiplies the loss in place
     # (models/shelgon3/Trainer.py:104)
-    return loss.clone(), z_q, perplexity.clone(), idx, hist
+    return F.vq_forward(z, E, beta, mode=mode)
 
 
 @_vq_forward_op.register_fake
@@ -101,8 +100,7 @@ class _VQFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z: Tensor, E: Tensor, beta: float, mode: str):
-        loss, z_q, perplexity, idx, hist = F.vq_forward(z, E, beta, mode=mode)
-        loss, perplexity = loss.clone(), perplexity.clone()    # fresh 0-d tensors (in-place scaling, Trainer.py:104)
+        loss, z_q, perplexity, idx, hist = F.vq_forward(z, E, beta, mode=mode)   # loss / perplexity: fresh 0-d tensors
         ctx.save_for_backward(z, E, idx, hist)
         ctx.beta = beta
         ctx.set_materialize_grads(False)
