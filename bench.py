@@ -717,7 +717,7 @@ def main():
     ap.add_argument("--no-refcuda", action="store_true")
     ap.add_argument("--no-kshard", action="store_true")
     ap.add_argument("--kshard-steps", type=int, default=4)
-    ap.add_argument("--chunk-rows", type=int, default=75776)  # 4 full waves of 74 CTA pairs x 256 rows
+    ap.add_argument("--chunk-rows", type=int, default=0)  # 0 = the library's default: one wave of the search kernel per chunk
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "kvq":
         args.warmup = 3          # timing rule: at least three warm-up steps

@@ -261,7 +261,8 @@ int kvq_change_percentage_of_elements(const int64_t* in, int64_t R, int64_t C, i
 /* End-to-end forward+backward with HOST buffers (pinned memory recommended): copies z and g_zq to the device
  * in row chunks, runs the layer, and copies z_q, idx, dz, loss, perplexity and dE back, overlapping copies with
  * compute on internal streams.  Synchronous: returns when every output is in host memory.
- * g_loss_host is the host scalar weight of the loss in the total objective. */
+ * g_loss_host is the host scalar weight of the loss in the total objective.
+ * rows_per_chunk <= 0 selects the default: one full wave of the search kernel per chunk (SMs / 2 * 256 rows). */
 int kvq_forward_backward_host(const float* z_host, const float* E_host, const float* g_zq_host, float g_loss_host,
                               int64_t N, int D, int64_t K, float beta, int mode,
                               float* z_q_host, int64_t* idx_host, float* loss_host, float* perplexity_host,

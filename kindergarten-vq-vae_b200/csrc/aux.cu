@@ -1,5 +1,8 @@
 // (1) token-id corruption helpers (common/tensor_utils.py:13-49, :52-87) with a counter-based device RNG;
 // (2) the host-buffer end-to-end entry point: row-chunked H2D / compute / D2H pipeline on three streams.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -170,30 +173,24 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   KVQ_REQUIRE(n_global >= N, KVQ_ERR_ARG, "kvq_forward_backward_host: n_global < N");
   KVQ_REQUIRE(N >= 1 && K >= 1 && D >= 4 && D % 4 == 0 && D <= 1024, KVQ_ERR_SHAPE,
               "kvq_forward_backward_host: bad shape N=%lld D=%d K=%lld", (long long)N, D, (long long)K);
-  if (rows_per_chunk <= 0) rows_per_chunk = 131072;
+  // Chunk boundaries.  Both copy directions move the same number of bytes and both are saturated for the whole call, so
+  // what the pipeline adds to the bare copy time is the head (nothing can return before the codebook and the first
+  // chunk have landed and been searched) plus the tail (what is still to do after the last upload), and how far the
+  // return stream trails the inbound one in between: one chunk's search plus one chunk's return copy.  The default chunk
+  // is therefore ONE full wave of the search kernel (a 256-latent tile per CTA pair: 18944 rows on 148 SMs) -- the
+  // smallest chunk the tensor cores sweep at full rate -- preceded by a short lead-in chunk (a sweep over the codebook
+  // takes the same time for any row count up to a wave, but a short chunk lands sooner).  Measured at N = 2^20, D = 256,
+  // K = 65536: 48.4 ms per call with one-wave chunks against 49.9 / 52.0 ms with 2 / 4 waves per chunk.
+  const int64_t wave = (int64_t)(sm_count() / 2) * 256;
+  if (rows_per_chunk <= 0) rows_per_chunk = wave >= 128 ? wave : 16384;
   rows_per_chunk = (rows_per_chunk + 127) / 128 * 128;
-  // Chunk boundaries.  The pipeline's exposed time is the first chunk's host->device copy (compute cannot start
-  // before it) plus the last chunk's device->host copy, so when the batch is large the first and the last chunk are
-  // shrunk to one full wave of the search kernel (one 256-latent tile per CTA pair); the middle stays coarse.
   std::vector<int64_t> bounds;
   {
-    const int64_t wave = (int64_t)(sm_count() / 2) * 256;
     bounds.push_back(0);
-    if (wave >= 128 && rows_per_chunk > wave && N >= 2 * wave + rows_per_chunk) {
-      // lead-in: the return direction moves as many bytes as the inbound one and cannot start before the first chunk has
-      // been searched, so the very first chunk is kept small (one sweep over the codebook takes the same time for any
-      // row count up to a full wave); then a one-wave chunk, then the coarse middle, then a one-wave tail
-      const int64_t lead = 4096;
-      if (lead < wave) bounds.push_back(lead);
-      bounds.push_back(wave);
-      while (bounds.back() + rows_per_chunk < N - wave) bounds.push_back(bounds.back() + rows_per_chunk);
-      if (bounds.back() < N - wave) bounds.push_back(N - wave);
-      if (lead < wave) bounds.push_back(N - lead);      // lead-out: little left to search and return after the last upload
-      bounds.push_back(N);
-    } else {
-      while (bounds.back() + rows_per_chunk < N) bounds.push_back(bounds.back() + rows_per_chunk);
-      bounds.push_back(N);
-    }
+    const int64_t lead = 4096;
+    if (rows_per_chunk > lead && N >= 4 * rows_per_chunk) bounds.push_back(lead);
+    while (bounds.back() + rows_per_chunk < N) bounds.push_back(bounds.back() + rows_per_chunk);
+    bounds.push_back(N);
   }
   const int64_t chunks = (int64_t)bounds.size() - 1;
   KVQ_REQUIRE(chunks <= 4096, KVQ_ERR_ARG, "kvq_forward_backward_host: too many chunks (%lld)", (long long)chunks);
@@ -221,14 +218,21 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   cudaEvent_t* ev_in = new cudaEvent_t[chunks];     // z chunk has landed (the search may start)
   cudaEvent_t* ev_g = new cudaEvent_t[chunks];      // upstream-gradient chunk has landed (needed by dz only)
   cudaEvent_t* ev_done = new cudaEvent_t[chunks];
-  cudaEvent_t ev_E, ev_final;
+  cudaEvent_t* ev_out = new cudaEvent_t[chunks];    // trace only: this chunk's device->host copies have finished
+  cudaEvent_t ev_E, ev_final, ev_start;
+  // KVQ_PIPE_TRACE=1: events keep timestamps and the per-chunk timeline is printed to stderr (a diagnostic, not a mode)
+  const char* trace_env = getenv("KVQ_PIPE_TRACE");
+  const bool trace = trace_env && trace_env[0] == '1';
+  const unsigned ev_flags = trace ? cudaEventDefault : cudaEventDisableTiming;
   for (int64_t c = 0; c < chunks; ++c) {
-    cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_g[c], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_in[c], ev_flags);
+    cudaEventCreateWithFlags(&ev_g[c], ev_flags);
+    cudaEventCreateWithFlags(&ev_done[c], ev_flags);
+    cudaEventCreateWithFlags(&ev_out[c], ev_flags);
   }
-  cudaEventCreateWithFlags(&ev_E, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&ev_final, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ev_E, ev_flags);
+  cudaEventCreateWithFlags(&ev_final, ev_flags);
+  cudaEventCreateWithFlags(&ev_start, ev_flags);
   int status = KVQ_OK;
 #define KVQ_TRY(expr)                                     \
   do {                                                    \
@@ -242,6 +246,7 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   } while (0)
 
   // inputs: codebook first, then latent / upstream-gradient chunks
+  if (trace) KVQ_TRYC(cudaEventRecord(ev_start, hp.s_in));
   KVQ_TRYC(cudaMemcpyAsync(hp.E, E_h, (size_t)K * D * 4, cudaMemcpyHostToDevice, hp.s_in));
   KVQ_TRYC(cudaMemcpyAsync(hp.scal + 2, &g_loss_h, 4, cudaMemcpyHostToDevice, hp.s_in));
   KVQ_TRYC(cudaEventRecord(ev_E, hp.s_in));
@@ -276,6 +281,7 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
     KVQ_TRYC(cudaMemcpyAsync(zq_h + r0 * D, hp.zq + r0 * D, (size_t)rows * D * 4, cudaMemcpyDeviceToHost, hp.s_out));
     KVQ_TRYC(cudaMemcpyAsync(dz_h + r0 * D, hp.dz + r0 * D, (size_t)rows * D * 4, cudaMemcpyDeviceToHost, hp.s_out));
     KVQ_TRYC(cudaMemcpyAsync(idx_h + r0, hp.idx + r0, (size_t)rows * 8, cudaMemcpyDeviceToHost, hp.s_out));
+    if (trace) KVQ_TRYC(cudaEventRecord(ev_out[c], hp.s_out));
   }
   if (status == KVQ_OK) {
     // loss / perplexity first: the internal sq_sum lives in the workspace the bucketed backward reuses
@@ -288,15 +294,33 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
       KVQ_TRYC(cudaMemcpyAsync(perp_h, hp.scal + 1, 4, cudaMemcpyDeviceToHost, hp.s_cmp));
       KVQ_TRYC(cudaMemcpyAsync(dE_h, dE, (size_t)K * D * 4, cudaMemcpyDeviceToHost, hp.s_cmp));
     }
+    if (trace) KVQ_TRYC(cudaEventRecord(ev_final, hp.s_cmp));
   }
   KVQ_TRYC(cudaStreamSynchronize(hp.s_in));
   KVQ_TRYC(cudaStreamSynchronize(hp.s_cmp));
   KVQ_TRYC(cudaStreamSynchronize(hp.s_out));
+  if (trace && status == KVQ_OK) {
+    float t_E = 0, t_fin = 0;
+    cudaEventElapsedTime(&t_E, ev_start, ev_E);
+    cudaEventElapsedTime(&t_fin, ev_start, ev_final);
+    fprintf(stderr, "kvq host pipeline: %lld chunks, codebook landed %.3f ms, all done %.3f ms\n", (long long)chunks, t_E, t_fin);
+    for (int64_t c = 0; c < chunks; ++c) {
+      float a = 0, b = 0, d = 0, o = 0;
+      cudaEventElapsedTime(&a, ev_start, ev_in[c]);
+      cudaEventElapsedTime(&b, ev_start, ev_g[c]);
+      cudaEventElapsedTime(&d, ev_start, ev_done[c]);
+      cudaEventElapsedTime(&o, ev_start, ev_out[c]);
+      fprintf(stderr, "  chunk %3lld rows %7lld  z in %7.3f  g in %7.3f  computed %7.3f  returned %7.3f\n", (long long)c,
+              (long long)(bounds[c + 1] - bounds[c]), a, b, d, o);
+    }
+  }
 #undef KVQ_TRY
 #undef KVQ_TRYC
-  for (int64_t c = 0; c < chunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_g[c]); cudaEventDestroy(ev_done[c]); }
-  cudaEventDestroy(ev_E); cudaEventDestroy(ev_final);
-  delete[] ev_in; delete[] ev_g; delete[] ev_done;
+  for (int64_t c = 0; c < chunks; ++c) {
+    cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_g[c]); cudaEventDestroy(ev_done[c]); cudaEventDestroy(ev_out[c]);
+  }
+  cudaEventDestroy(ev_E); cudaEventDestroy(ev_final); cudaEventDestroy(ev_start);
+  delete[] ev_in; delete[] ev_g; delete[] ev_done; delete[] ev_out;
   return status;
 }
 

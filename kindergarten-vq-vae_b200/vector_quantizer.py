@@ -124,6 +124,25 @@ class _VQFunction(torch.autograd.Function):
         return dz, dE, None, None
 
 
+class _EmptyBatchFunction(torch.autograd.Function):
+    """A batch with no latents.  The reference then takes means over zero elements (VectorQuantizer.py:76-85): loss and
+    perplexity are NaN, every other output is empty, and autograd gives the codebook an all-zero gradient."""
+
+    @staticmethod
+    def forward(ctx, z: Tensor, E: Tensor):
+        ctx.save_for_backward(E)
+        ctx.set_materialize_grads(False)
+        nan = torch.full((), float("nan"), dtype=torch.float32, device=z.device)
+        idx = torch.empty(0, dtype=torch.int64, device=z.device)
+        ctx.mark_non_differentiable(idx)
+        return nan, torch.empty_like(z), nan.clone().detach(), idx
+
+    @staticmethod
+    def backward(ctx, g_loss, g_zq, g_perp, g_idx):
+        (E,) = ctx.saved_tensors
+        return (g_zq if ctx.needs_input_grad[0] else None), (torch.zeros_like(E) if ctx.needs_input_grad[1] else None)
+
+
 class VectorQuantizer(nn.Module):
     """
     Discretization bottleneck part of the VQ-VAE (B200-native).
@@ -176,7 +195,9 @@ class VectorQuantizer(nn.Module):
             raise RuntimeError("VectorQuantizer (kvq) runs on CUDA only: there is no CPU fallback "
                                f"(z on {z.device}, codebook on {weight.device})")
         N = z_flattened.shape[0]
-        if torch.compiler.is_compiling():      # traced (model.compile(), main.py:83): one opaque dispatcher node
+        if N == 0:
+            loss, z_q, perplexity, idx = _EmptyBatchFunction.apply(z_flattened, weight)
+        elif torch.compiler.is_compiling():      # traced (model.compile(), main.py:83): one opaque dispatcher node
             loss, z_q, perplexity, idx, _hist = _vq_forward_op(z_flattened, weight, float(self.beta), self.search)
         else:                                  # eager: same C-ABI calls without the operator-dispatch overhead
             loss, z_q, perplexity, idx, _hist = _VQFunction.apply(z_flattened, weight, float(self.beta), self.search)

@@ -150,6 +150,20 @@ def test_fp32_only_shape_and_shape_errors():
         vq.forward(torch.randn(4, 6, 32, device=DEV).transpose(0, 1), DEV)   # non-contiguous: .view fails like the reference
 
 
+def test_empty_batch_like_the_reference():
+    """No latents at all: the reference's means over zero elements give NaN loss / perplexity, empty tensors everywhere
+    else, and autograd hands the codebook an all-zero gradient (VectorQuantizer.py:55-93 run on a (0, S, D) input)."""
+    k = _kvq()
+    vq = k.VectorQuantizer(8, 32, 0.25).to(DEV)
+    z = torch.zeros(0, 3, 32, device=DEV, requires_grad=True)
+    loss, z_q, perp, onehot, idx = vq.forward(z, DEV)
+    assert loss.shape == () and torch.isnan(loss) and perp.shape == () and torch.isnan(perp)
+    assert z_q.shape == (0, 3, 32) and idx.shape == (0, 3, 1) and idx.dtype == torch.int64
+    assert onehot is not None and onehot.shape == (0, 8)
+    (loss + z_q.sum()).backward()
+    assert float(vq.embedding.weight.grad.abs().max()) == 0.0 and z.grad.shape == (0, 3, 32)
+
+
 def test_frozen_encoder_and_eval_modes():
     k = _kvq()
     z, E, gz = _seeded(4, 16, 64, 32, "normal")
