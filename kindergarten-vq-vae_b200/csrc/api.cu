@@ -121,7 +121,7 @@ int run_search(int mode, const float* z, const float* E, const float* e2, const 
   if (mode == KVQ_SEARCH_TF32_REFINE && tf32_refine_on_tensor_cores(N, D, K)) {
     // tensor-core search keeping the two best codes per latent, then an exact float64 re-evaluation of the pair
     int64_t* runner_up = reinterpret_cast<int64_t*>(scratch);
-    int rc = launch_search_tf32_top2(z, E, e2, N, D, K, idx, runner_up, st);
+    int rc = launch_search_tf32_top2(z, E, e2, N, D, K, idx, runner_up, st, e2max);
     if (rc) return rc;
     if (deferred) { *deferred = 1; return KVQ_OK; }   // fused into the gather kernel by the caller
     return launch_refine_top2(z, E, N, D, idx, runner_up, e2max, st);

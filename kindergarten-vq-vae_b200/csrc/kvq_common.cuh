@@ -192,7 +192,7 @@ bool tf32_shape_ok(int64_t N, int D, int64_t K);
 bool tf32_refine_on_tensor_cores(int64_t N, int D, int64_t K);   // else the default mode uses the (exact) fp32 search
 bool tf32_operands_rounded();   // TMA rounds fp32 -> tf32 to nearest (default) instead of the MMA truncating
 int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
-                            int64_t* idx, int64_t* idx2, cudaStream_t st);
+                            int64_t* idx, int64_t* idx2, cudaStream_t st, const float* e2max = nullptr);
 int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2,
                        const float* e2max, cudaStream_t st);
 // unsharded search in any mode (AUTO already resolved): idx out; `scratch` = N int64 (keys / packed runner-up words).

@@ -76,6 +76,8 @@ struct Params {
   const float* e2;      // padded to n_tiles*256 with +inf
   int64_t* idx;
   int64_t* idx2;        // TOP2 kernels: runner-up code per latent (for the exact re-evaluation pass)
+  const float* e2max;   // TOP2 kernels, optional: max_k |E_k|^2 -> the epilogue only tracks runner-up candidates that
+  float tau_c;          //   lie within tau_i = tau_c |z_i| max|E| + 2^-15 max|E|^2 of the row's running best
   long long* keys;
   PeerKeys peers;       // n > 0: MIN-combine the packed keys straight into every rank's buffer over NVLink
   // EPI_STORE only: out (N x ldc) receives alpha * (z E^T) + bias for columns < K, zeros for columns in [K, ldc)
@@ -271,6 +273,16 @@ __device__ __forceinline__ float batch_scores(const uint32_t (&acc)[32], const f
   const float u3 = fmin2(t[9], t[10]);
   return fmin2(fmin3(u0, u1, u2), u3);
 }
+
+// The epilogue's code size matters as much as its instruction count: the per-batch code below is instantiated once per
+// register buffer of the software pipeline, eight warps walk it at different places, and a body of several thousand
+// instructions (the first top-2 epilogue was 100 KB of SASS) stalls them on instruction fetch.  So the paths that are
+// rare by construction (a NaN score) are real functions working on a stack copy of the 32 scores.
+__device__ __noinline__ int first_nan_column(const float* s) {
+  for (int jj = 0; jj < 31; ++jj)
+    if (s[jj] != s[jj]) return jj;
+  return 31;
+}
 // first column of the batch attaining the minimum m (first NaN column when m is NaN)
 __device__ __forceinline__ int first_column_of(const float (&s)[32], float m) {
   int j = 31;
@@ -278,8 +290,10 @@ __device__ __forceinline__ int first_column_of(const float (&s)[32], float m) {
 #pragma unroll
     for (int jj = 30; jj >= 0; --jj) j = (s[jj] == m) ? jj : j;
   } else {
+    float tmp[32];
 #pragma unroll
-    for (int jj = 30; jj >= 0; --jj) j = (s[jj] != s[jj]) ? jj : j;
+    for (int jj = 0; jj < 32; ++jj) tmp[jj] = s[jj];
+    j = first_nan_column(tmp);
   }
   return j;
 }
@@ -306,29 +320,49 @@ __device__ __forceinline__ void argmin_batch(const uint32_t (&acc)[32], const fl
 struct Top2 {
   float bv, b2v, ov;
   uint32_t bi, b2i, oi;
+  float tau;   // half-width of the band above the running best inside which a runner-up can still matter (+inf: no filter)
+  float thr;   // min(ov, bv + tau): a batch minimum at or above it changes nothing
 };
+// Slow-path filter.  The exact pass re-evaluates a pair only when its tf32 score gap is inside the row's error bound
+// (bandwidth_kernels.cu: refine_inside_bound), so a candidate whose score is more than tau above the running best can
+// never matter as a runner-up: the best only decreases.  tau is a slightly inflated copy of that bound (the epilogue forms
+// |z_i| from the tf32-rounded tile in shared memory), so everything the exact pass would look at is still tracked.
+// Without the filter a batch entered the slow path whenever it held one of the row's two best scores so far
+// (probability 2/j at the j-th batch, OR-ed over the 32 rows of the warp: 108 of the 128 batches of a K = 8192 sweep);
+// with it, essentially only when the best itself improves, and the second-best scan inside the batch runs only when a
+// second column is inside the band.
 __device__ __forceinline__ void argmin_batch_top2(const uint32_t (&acc)[32], const float4* __restrict__ e2v,
                                                   uint32_t col_base, Top2& t) {
   float s[32];
   const float m = batch_scores(acc, e2v, s);
-  if (!(m >= t.bv)) {
+  if (!(m >= t.thr)) {
     if (t.bv == t.bv) {
-      // the previous winner becomes a candidate of the "other batches" slot (its own batch's runner-up cannot beat it)
-      if (t.bv < t.ov || (t.bv == t.ov && t.bi < t.oi)) { t.ov = t.bv; t.oi = t.bi; }
       const int j = first_column_of(s, m);
-      t.bv = m;
-      t.bi = col_base + (uint32_t)j;
-      float r = INFINITY;
-      int rj = 0;
+      if (!(m >= t.bv)) {
+        // the previous winner becomes a candidate of the "other batches" slot (its own batch's runner-up cannot beat it)
+        if (t.bv < t.ov || (t.bv == t.ov && t.bi < t.oi)) { t.ov = t.bv; t.oi = t.bi; }
+        t.bv = m;
+        t.bi = col_base + (uint32_t)j;
+        const float lim = m + t.tau;
+        int n_close = 0;
 #pragma unroll
-      for (int jj = 31; jj >= 0; --jj)
-        if (jj != j && s[jj] <= r) { r = s[jj]; rj = jj; }     // '<=' while walking down: first index wins ties
-      t.b2v = r;
-      t.b2i = col_base + (uint32_t)rj;
+        for (int jj = 0; jj < 32; ++jj) n_close += (s[jj] <= lim) ? 1 : 0;
+        float r = INFINITY;
+        int rj = 0;
+        if (n_close != 1) {    // another column inside the band -- one trigger in ten per row: the band is a few
+                               // percent of the score spread -- (or a NaN winner: irrelevant then)
+#pragma unroll
+          for (int jj = 31; jj >= 0; --jj)
+            if (jj != j && s[jj] <= r) { r = s[jj]; rj = jj; }     // '<=' while walking down: first index wins ties
+        }
+        t.b2v = r;
+        t.b2i = col_base + (uint32_t)rj;
+      } else {                 // bv <= m < min(ov, bv + tau): best runner-up candidate from another batch so far
+        t.ov = m;
+        t.oi = col_base + (uint32_t)j;
+      }
+      t.thr = fminf(t.ov, t.bv + t.tau);
     }
-  } else if (m < t.ov) {
-    t.ov = m;
-    t.oi = col_base + (uint32_t)first_column_of(s, m);
   }
 }
 
@@ -383,9 +417,11 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
+    // the top-2 epilogue reads the resident latent tile (row norms): its 8 warps release each block too
+    const uint32_t a_readers = (EPI == EPI_TOP2 && p.e2max != nullptr) ? 1u + NUM_EPI_WARPS : 1u;
     for (int kb = 0; kb < MAX_A_KBLOCKS; ++kb) {
       mbar_init(bar_a_full + 8 * kb, 1);
-      mbar_init(bar_a_empty + 8 * kb, 1);
+      mbar_init(bar_a_empty + 8 * kb, a_readers);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tm_full + 8 * a, 1);
@@ -591,7 +627,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
       float bv = INFINITY;
       uint32_t bi = (uint32_t)(t_begin * BLOCK_N + half * 128);
       Top2 t2;
-      t2.bv = t2.b2v = t2.ov = INFINITY;
+      t2.bv = t2.b2v = t2.ov = t2.tau = t2.thr = INFINITY;
       t2.bi = t2.b2i = t2.oi = bi;
 
       for (int t = t_begin; t < t_end; ++t) {
@@ -600,27 +636,56 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
         const uint32_t col0 = (uint32_t)(t * BLOCK_N + half * 128);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * 128;
         const float4* e2v = reinterpret_cast<const float4*>(p.e2 + col0);
+        if constexpr (TOP2) {
+          if (t == t_begin && p.e2max != nullptr && p.resident) {
+            // |z_row|^2 from the resident tile.  The first accumulator of the item is complete, so every block of the
+            // tile has landed (in both CTAs) and none can be replaced before this warp releases it below.  The 128-byte
+            // swizzle only permutes the 16-byte chunks inside a row; lanes start at different chunks (no bank conflicts).
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            const uint8_t* arow = smem + SMEM_CTRL_BYTES + row_in_tile * 128;
+            float z2 = 0.f;
+            for (int kb = 0; kb < p.num_kblocks; ++kb) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(arow + kb * A_KBLOCK_BYTES + (((c + lane) & 7) << 4));
+                z2 = fmaf(v.x, v.x, z2); z2 = fmaf(v.y, v.y, z2); z2 = fmaf(v.z, v.z, z2); z2 = fmaf(v.w, v.w, z2);
+              }
+            }
+            __syncwarp();
+            if (lane == 0)
+              for (int kb = 0; kb < p.num_kblocks; ++kb) mbar_arrive(bar_a_empty + 8 * kb);
+            const float e2m = __ldg(p.e2max);
+            t2.tau = fmaf(p.tau_c, sqrtf(z2 * e2m), 3.0517578125e-5f * e2m);   // NaN / inf norms: tau = NaN or inf, see thr
+            if (!(t2.tau == t2.tau)) t2.tau = INFINITY;
+          }
+        }
         // software pipeline over the four 32-column batches: the TMEM load of batch b+1 is in flight while batch b
         // is reduced; the accumulator is handed back to the MMA as soon as the last load has landed.
+        // (a rolled loop of two steps, each reducing one batch per register buffer: two copies of the per-batch code
+        // instead of four -- see the note on code size above)
         uint32_t ra[32], rb[32];
         tmem_ld32_async(taddr, ra);
         tmem_wait_ld(ra);
-        tmem_ld32_async(taddr + 32, rb);
-        if constexpr (TOP2) argmin_batch_top2(ra, e2v, col0, t2); else argmin_batch(ra, e2v, col0, bv, bi);
-        tmem_wait_ld(rb);
-        tmem_ld32_async(taddr + 64, ra);
-        if constexpr (TOP2) argmin_batch_top2(rb, e2v + 8, col0 + 32, t2); else argmin_batch(rb, e2v + 8, col0 + 32, bv, bi);
-        tmem_wait_ld(ra);
-        tmem_ld32_async(taddr + 96, rb);
-        if constexpr (TOP2) argmin_batch_top2(ra, e2v + 16, col0 + 64, t2); else argmin_batch(ra, e2v + 16, col0 + 64, bv, bi);
-        tmem_wait_ld(rb);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (CG == 2) mbar_arrive_cluster(map_to_cta(bar_tm_empty + 8 * acc, 0));
-          else mbar_arrive(bar_tm_empty + 8 * acc);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld32_async(taddr + 32 + 64 * h, rb);
+          if constexpr (TOP2) argmin_batch_top2(ra, e2v + 16 * h, col0 + 64 * h, t2);
+          else argmin_batch(ra, e2v + 16 * h, col0 + 64 * h, bv, bi);
+          tmem_wait_ld(rb);
+          if (h == 0) {
+            tmem_ld32_async(taddr + 64, ra);
+          } else {             // the last load has landed: hand the accumulator back to the MMA
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster(map_to_cta(bar_tm_empty + 8 * acc, 0));
+              else mbar_arrive(bar_tm_empty + 8 * acc);
+            }
+          }
+          if constexpr (TOP2) argmin_batch_top2(rb, e2v + 8 + 16 * h, col0 + 32 + 64 * h, t2);
+          else argmin_batch(rb, e2v + 8 + 16 * h, col0 + 32 + 64 * h, bv, bi);
+          if (h == 0) tmem_wait_ld(ra);
         }
-        if constexpr (TOP2) argmin_batch_top2(rb, e2v + 24, col0 + 96, t2); else argmin_batch(rb, e2v + 24, col0 + 96, bv, bi);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -751,7 +816,7 @@ static int env_int(const char* name, int dflt) {
 template <int CG, int EPI>
 static int launch_cg(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t k_offset,
                      int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st, const PeerKeys* peers,
-                     int64_t* idx2) {
+                     int64_t* idx2, const float* e2max = nullptr) {
   constexpr int B_STAGE_BYTES = (BLOCK_N / CG) * BLOCK_K * 4;
   Params p;
   p.N = N; p.K = K; p.k_offset = k_offset; p.D = D;
@@ -777,6 +842,8 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   p.stages = stages;
   p.use_atomic = (p.ksplit > 1 || keys_accumulate) ? 1 : 0;
   p.e2 = e2; p.idx = idx; p.keys = keys; p.idx2 = idx2;
+  p.e2max = (EPI == EPI_TOP2 && p.resident && env_int("KVQ_TOP2_FILTER", 1) != 0) ? e2max : nullptr;   // 0: A/B switch
+  p.tau_c = 1.25f * 0.00390625f * (tf32_operands_rounded() ? 1.f : 2.f);   // refine_bound_c2() uses 1.125: strictly wider
   if (peers) p.peers = *peers; else p.peers.n = 0;
   p.out = nullptr; p.ldc = 0; p.bias = nullptr; p.alpha = 1.f;
   constexpr bool TOP2 = (EPI == EPI_TOP2);
@@ -926,12 +993,12 @@ bool tf32_refine_on_tensor_cores(int64_t N, int D, int64_t K) {
 }
 
 int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
-                            int64_t* idx, int64_t* idx2, cudaStream_t st) {
+                            int64_t* idx, int64_t* idx2, cudaStream_t st, const float* e2max) {
   if (N <= 0) return KVQ_OK;
   KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (got D=%d)", D);
   KVQ_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)E & 15) == 0, KVQ_ERR_ARG,
               "tf32 search needs 16-byte aligned z and E (TMA)");
-  return t5::launch_cg<2, t5::EPI_TOP2>(z, E, e2, N, D, K, 0, idx, nullptr, 0, st, nullptr, idx2);
+  return t5::launch_cg<2, t5::EPI_TOP2>(z, E, e2, N, D, K, 0, idx, nullptr, 0, st, nullptr, idx2, e2max);
 }
 
 }  // namespace kvq

@@ -206,7 +206,12 @@ class VectorQuantizer(nn.Module):
         want = self.return_min_encodings
         if want == "auto":
             want = N * self.n_e * 4 <= ONEHOT_AUTO_BYTES
-        min_encodings = (_onehot_op(idx, self.n_e) if torch.compiler.is_compiling() else F.onehot(idx, self.n_e)) if want else None    # VectorQuantizer.py:67-68
+        if not want:
+            min_encodings = None
+        elif N == 0:
+            min_encodings = z.new_zeros((0, self.n_e), dtype=torch.float32)
+        else:                                                                    # VectorQuantizer.py:67-68
+            min_encodings = _onehot_op(idx, self.n_e) if torch.compiler.is_compiling() else F.onehot(idx, self.n_e)
 
         min_encoding_indices = idx.reshape((batch_size, seq_len, 1))  # VectorQuantizer.py:90
         return loss, z_q, perplexity, min_encodings, min_encoding_indices
