@@ -308,7 +308,6 @@ def run_kvq(args):
 
     for _ in range(args.warmup):
         step()
-    sync_all()
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream, max over ranks -------------
     lib.kvq_profile_enable(1)
@@ -316,6 +315,10 @@ def run_kvq(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the barrier comes LAST before the start event: anything a rank does between the barrier and its first launch
+    # (starting the clock sampler took a rank-dependent 5-15 ms) is charged to the other ranks, which wait for it in the
+    # first collective, and the max over ranks would report that skew as step time
+    sync_all()
     e0.record()
     for _ in range(args.steps):
         loss, perp = step()

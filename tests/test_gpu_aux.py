@@ -117,6 +117,31 @@ def test_host_end_to_end_other_shapes(N, D, K, mode):
     F._lib.load().kvq_host_release()
 
 
+def test_host_end_to_end_default_chunking_equals_device_path():
+    """rows_per_chunk = 0: the library's own chunking (a short lead-in chunk, then one full wave of the search kernel per
+    chunk, ragged tail).  Every output must equal the device-resident path's on the same rows."""
+    k = _kvq()
+    F = k.functional
+    gen = torch.Generator().manual_seed(5)
+    N, D, K = 100_000, 64, 300            # > 4 waves of 18944 rows: lead-in + 5 full chunks + a ragged last one
+    z = torch.randn(N, D, generator=gen).pin_memory()
+    E = torch.randn(K, D, generator=gen).pin_memory()
+    g = torch.randn(N, D, generator=gen).pin_memory()
+    out = F.forward_backward_host(z, E, g, 0.8, 0.25, mode="auto", rows_per_chunk=0)
+    zd, Ed, gd = z.to(DEV), E.to(DEV), g.to(DEV)
+    loss, z_q, perp, idx, hist = F.vq_forward(zd, Ed, 0.25, mode="auto")
+    dz, dE = F.vq_backward(zd, Ed, idx, hist, 0.25, g_zq=gd, g_loss=torch.tensor(0.8, device=DEV))
+    assert torch.equal(out["idx"], idx.cpu())              # default mode: exact pass, chunking cannot change a row's result
+    assert torch.equal(out["z_q"], z_q.cpu()) and torch.allclose(out["dz"], dz.cpu(), rtol=1e-6, atol=1e-8)
+    assert abs(float(out["loss"]) - float(loss)) <= 1e-6 * float(loss)
+    assert abs(float(out["perplexity"]) - float(perp)) <= 1e-6 * float(perp)
+    assert (out["dE"] - dE.cpu()).abs().max() <= 1e-5 * dE.abs().max()
+    rows = torch.arange(0, N, 97)
+    ref = O.forward_fp32(z[rows], E, 0.25)
+    assert O.index_parity(out["idx"][rows], ref.idx, z[rows], E).unexcused == 0
+    F._lib.load().kvq_host_release()
+
+
 def test_kmeans2_matches_scipy_given_the_same_initial_centroids():
     """Device Lloyd iterations vs scipy.cluster.vq.kmeans2 (the call of vq_codebook_init_weights.py:85)."""
     from scipy.cluster.vq import kmeans2 as sp_kmeans2

@@ -116,6 +116,7 @@ SHAPES = [
     (1, 5000, 32, 3000, "normal"),      # narrowest D the tensor-core kernel takes
     (2, 300, 256, 2048, "collapsed"),
     (1, 200, 256, 16384, "normal"),     # few latents, many codes: code-range split + atomicMin merge
+    (2, 300, 64, 140000, "normal"),     # code indices beyond 16 bits (K-sharded shards are this size), K % 256 != 0
 ]
 
 
