@@ -287,8 +287,18 @@ __device__ __noinline__ int first_nan_column(const float* s) {
 __device__ __forceinline__ int first_column_of(const float (&s)[32], float m) {
   int j = 31;
   if (m == m) {
+    // four independent 8-column scans and a 4-way pick: the same compares and selects as one 31-step scan, but a
+    // dependency chain of 11 instead of 31 -- the slow path's latency is what delays handing the accumulator back
+    int g[4];
 #pragma unroll
-    for (int jj = 30; jj >= 0; --jj) j = (s[jj] == m) ? jj : j;
+    for (int q = 0; q < 4; ++q) {
+      int c = 32;
+#pragma unroll
+      for (int jj = 7; jj >= 0; --jj) c = (s[8 * q + jj] == m) ? 8 * q + jj : c;
+      g[q] = c;
+    }
+    j = min(min(g[0], g[1]), min(g[2], g[3]));
+    j = min(j, 31);
   } else {
     float tmp[32];
 #pragma unroll
@@ -344,9 +354,10 @@ __device__ __forceinline__ void argmin_batch_top2(const uint32_t (&acc)[32], con
         t.bv = m;
         t.bi = col_base + (uint32_t)j;
         const float lim = m + t.tau;
-        int n_close = 0;
+        int nc[4] = {0, 0, 0, 0};   // four short chains, like the column scan
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) n_close += (s[jj] <= lim) ? 1 : 0;
+        for (int jj = 0; jj < 32; ++jj) nc[jj & 3] += (s[jj] <= lim) ? 1 : 0;
+        const int n_close = (nc[0] + nc[1]) + (nc[2] + nc[3]);
         float r = INFINITY;
         int rj = 0;
         if (n_close != 1) {    // another column inside the band -- one trigger in ten per row: the band is a few
