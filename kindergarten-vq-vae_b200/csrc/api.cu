@@ -72,7 +72,7 @@ int check_device() {
 
 static inline int64_t pad_codes(int64_t K) { return (K + SEARCH_TILE_N - 1) / SEARCH_TILE_N * SEARCH_TILE_N; }
 
-struct FwdWs { float* e2; long long* keys; double* sq_sum; float* e2max; size_t bytes; };
+struct FwdWs { float* e2; long long* keys; double* sq_sum; float* e2max; void* tail_rec; size_t bytes; };
 static FwdWs carve_forward(void* ws, int64_t N, int64_t K) {
   FwdWs w;
   char* p = static_cast<char*>(ws);
@@ -82,6 +82,8 @@ static FwdWs carve_forward(void* ws, int64_t N, int64_t K) {
   w.sq_sum = reinterpret_cast<double*>(p + off);
   w.e2max = reinterpret_cast<float*>(p + off + 8);
   off += 256;
+  w.tail_rec = p + off;                             // top-2 search: records of the split tail round
+  off += TOP2_TAIL_REC_BYTES;
   w.bytes = off;
   return w;
 }
@@ -115,13 +117,13 @@ static int resolve_mode(int mode, int64_t N, int D, int64_t K, int* out, bool al
 }
 
 int run_search(int mode, const float* z, const float* E, const float* e2, const float* e2max, int64_t N, int D, int64_t K,
-               int64_t* idx, long long* scratch, cudaStream_t st, int* deferred) {
+               int64_t* idx, long long* scratch, cudaStream_t st, int* deferred, void* tail_rec) {
   if (deferred) *deferred = 0;
   if (mode == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, e2, N, D, K, 0, idx, scratch, 0, st);
   if (mode == KVQ_SEARCH_TF32_REFINE && tf32_refine_on_tensor_cores(N, D, K)) {
     // tensor-core search keeping the two best codes per latent, then an exact float64 re-evaluation of the pair
     int64_t* runner_up = reinterpret_cast<int64_t*>(scratch);
-    int rc = launch_search_tf32_top2(z, E, e2, N, D, K, idx, runner_up, st, e2max);
+    int rc = launch_search_tf32_top2(z, E, e2, N, D, K, idx, runner_up, st, e2max, tail_rec);
     if (rc) return rc;
     if (deferred) { *deferred = 1; return KVQ_OK; }   // fused into the gather kernel by the caller
     return launch_refine_top2(z, E, N, D, idx, runner_up, e2max, st);
@@ -207,7 +209,7 @@ int kvq_search(const float* z, const float* E, int64_t N, int D, int64_t K, int6
   if (m == KVQ_SEARCH_TF32_REFINE) {
     KVQ_REQUIRE(k_offset == 0 && !keys && idx, KVQ_ERR_UNSUPPORTED,
                 "kvq_search: tf32_refine is for unsharded searches that return indices (no keys, k_offset 0)");
-    return run_search(m, z, E, w.e2, w.e2max, N, D, K, idx, w.keys, st);
+    return run_search(m, z, E, w.e2, w.e2max, N, D, K, idx, w.keys, st, nullptr, w.tail_rec);
   }
   if (m == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
   return launch_search_fp32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
@@ -311,7 +313,7 @@ static int forward_partials(const char* who, const float* z, const float* E, int
     rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, sq_sum, hist, st, nullptr, nullptr, nullptr, w.keys);
   } else {
     int deferred = 0;   // tf32_refine: the exact top-2 re-evaluation rides along in the gather kernel
-    rc = run_search(m, z, E, w.e2, w.e2max, N, D, K, idx, w.keys, st, &deferred);
+    rc = run_search(m, z, E, w.e2, w.e2max, N, D, K, idx, w.keys, st, &deferred, w.tail_rec);
     if (rc) return rc;
     ProfScope ps(KVQ_PROF_QUANTIZE, st);
     rc = launch_quantize(z, E, idx, N, D, K, 0, 0, z_q, sq_sum, hist, st, nullptr,

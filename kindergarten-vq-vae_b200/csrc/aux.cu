@@ -212,6 +212,7 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
   char* tail = wp + align_up((size_t)K_pad * 4, 256) + align_up((size_t)N * 8, 256);
   double* sq_sum = sharded ? sq_dev : reinterpret_cast<double*>(tail);
   float* e2max = reinterpret_cast<float*>(tail + 8);
+  void* tail_rec = tail + 256;
   int32_t* hist = sharded ? hist_dev : hp.hist;
   float* dE = sharded ? dE_dev : hp.dE;
 
@@ -266,7 +267,7 @@ static int host_pipeline(const float* z_h, const float* E_h, const float* g_h, f
     const int64_t r0 = bounds[c], rows = bounds[c + 1] - bounds[c];
     KVQ_TRYC(cudaStreamWaitEvent(hp.s_cmp, ev_in[c], 0));
     int deferred = 0;
-    KVQ_TRY(run_search(m, hp.z + r0 * D, hp.E, e2, e2max, rows, D, K, hp.idx + r0, keys + r0, hp.s_cmp, &deferred));
+    KVQ_TRY(run_search(m, hp.z + r0 * D, hp.E, e2, e2max, rows, D, K, hp.idx + r0, keys + r0, hp.s_cmp, &deferred, tail_rec));
     KVQ_TRY(launch_quantize(hp.z + r0 * D, hp.E, hp.idx + r0, rows, D, K, 0, 0, hp.zq + r0 * D, sq_sum, hist, hp.s_cmp,
                             nullptr, deferred ? reinterpret_cast<const int64_t*>(keys + r0) : nullptr,
                             deferred ? e2max : nullptr));

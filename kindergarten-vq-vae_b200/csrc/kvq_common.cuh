@@ -192,14 +192,18 @@ bool tf32_shape_ok(int64_t N, int D, int64_t K);
 bool tf32_refine_on_tensor_cores(int64_t N, int D, int64_t K);   // else the default mode uses the (exact) fp32 search
 bool tf32_operands_rounded();   // TMA rounds fp32 -> tf32 to nearest (default) instead of the MMA truncating
 int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
-                            int64_t* idx, int64_t* idx2, cudaStream_t st, const float* e2max = nullptr);
+                            int64_t* idx, int64_t* idx2, cudaStream_t st, const float* e2max = nullptr,
+                            void* tail_rec = nullptr);
+// workspace block of the top-2 search's tail items (see search_tf32.cu: Params): 16 bytes per row and code range, at most
+// one persistent round of rows (SMs / 2 groups of 256) -- sized for 256 SMs
+constexpr size_t TOP2_TAIL_REC_BYTES = (size_t)128 * 256 * 16;
 int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2,
                        const float* e2max, cudaStream_t st);
 // unsharded search in any mode (AUTO already resolved): idx out; `scratch` = N int64 (keys / packed runner-up words).
 // tf32_refine: with `deferred` the exact re-evaluation of the top-2 pair is left to launch_quantize (pass it `scratch`
 // as idx2); *deferred says whether that is still owed.  Without it the stand-alone refine kernel runs here.
 int run_search(int mode, const float* z, const float* E, const float* e2, const float* e2max, int64_t N, int D, int64_t K,
-               int64_t* idx, long long* scratch, cudaStream_t st, int* deferred = nullptr);
+               int64_t* idx, long long* scratch, cudaStream_t st, int* deferred = nullptr, void* tail_rec = nullptr);
 // C (M x ldc) = alpha * A (M x Kc) B^T (n x Kc) + bias on the tcgen05 tf32 path; Kc % 32 == 0, ldc % 4 == 0
 int launch_gemm_nt_tf32(const float* A, const float* B, int64_t M, int64_t n, int Kc, float* C, int64_t ldc,
                         const float* bias, float alpha, cudaStream_t st);

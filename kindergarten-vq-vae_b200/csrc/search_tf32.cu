@@ -54,6 +54,7 @@ constexpr int SMEM_LIMIT = 232448;                  // 227 KB opt-in maximum per
 constexpr int SMEM_CTRL_BYTES = 1024 + 1024;        // barriers + tmem slot | cross-half merge scratch
 constexpr int RESIDENT_MAX_D = 256;
 constexpr int MAX_A_KBLOCKS = RESIDENT_MAX_D / BLOCK_K;   // 8
+constexpr int TAIL_MIN_TILES = 8;                   // code tiles per tail item, at least
 static_assert(16 * MAX_STAGES + 16 * MAX_A_KBLOCKS + 32 + 4 <= 1024, "control block overflows its kilobyte");
 
 // tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor bit layout): c_format F32 @4, a/b_format TF32 @7/@10,
@@ -69,7 +70,16 @@ struct Params {
   int n_tiles;          // ceil(K / 256)
   int tiles_per_split;  // code tiles per item
   int ksplit;
-  int64_t n_items;      // ceil(m_tiles / CG) * ksplit
+  int64_t n_items;      // main_items + tail items
+  // Items [0, main_items) sweep `tiles_per_split` code tiles of row group item / ksplit.  Items beyond that are the TAIL
+  // (top-2 search only): the row groups of the last, partly filled round of the persistent grid, each cut into tail_split
+  // code ranges so that the round takes 1 / tail_split of a sweep instead of a whole one with most SMs idle.  A tail item
+  // leaves (best, runner-up) of its code range in tail_rec; a small kernel merges the ranges afterwards.
+  int64_t main_items;
+  int64_t tail_group0;  // first row group of the tail
+  int tail_split, tail_tiles;
+  uint4* tail_rec;      // [tail_split][tail_rows]: {best score, best column, runner-up score, runner-up column}
+  int64_t tail_rows;
   int resident;         // latent tile resident in smem
   int stages;
   int use_atomic;       // MIN-combine into keys (split code range or caller-accumulated keys)
@@ -86,6 +96,32 @@ struct Params {
   const float* bias;
   float alpha;
 };
+
+struct Item {
+  int64_t m_group;
+  int t_begin, t_end;
+  int tail_ks;          // >= 0: tail item, its code-range number
+};
+__device__ __forceinline__ Item decode_item(const Params& p, int64_t item) {
+  Item it;
+  int tiles;
+  int ks;
+  if (item < p.main_items) {
+    it.m_group = item / p.ksplit;
+    ks = (int)(item % p.ksplit);
+    tiles = p.tiles_per_split;
+    it.tail_ks = -1;
+  } else {
+    const int64_t ti = item - p.main_items;
+    it.m_group = p.tail_group0 + ti / p.tail_split;
+    ks = (int)(ti % p.tail_split);
+    tiles = p.tail_tiles;
+    it.tail_ks = ks;
+  }
+  it.t_begin = ks * tiles;
+  it.t_end = min(p.n_tiles, it.t_begin + tiles);
+  return it;
+}
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -467,11 +503,9 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
     const uint64_t pol_z = l2_policy_evict_first(), pol_e = l2_policy_evict_last();
     // completion bytes of both CTAs are counted on the leader's barriers
     for (int64_t item = first_item; item < p.n_items; item += item_stride) {
-      const int64_t m_group = item / p.ksplit;
-      const int ks = (int)(item % p.ksplit);
-      const int m0 = (int)((m_group * CG + cta_rank) * BLOCK_M);
-      const int t_begin = ks * p.tiles_per_split;
-      const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+      const Item it = decode_item(p, item);
+      const int m0 = (int)((it.m_group * CG + cta_rank) * BLOCK_M);
+      const int t_begin = it.t_begin, t_end = it.t_end;
       for (int t = t_begin; t < t_end; ++t) {
         const int n0 = t * BLOCK_N + (int)cta_rank * B_ROWS;
         // While the item's LAST code tile is being multiplied, pull the next item's latent tile into L2: its blocks
@@ -479,7 +513,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
         if (p.resident && t == t_end - 1 && item + item_stride < p.n_items) {
           if (elect_one()) {
             const int64_t nitem = item + item_stride;
-            const int nm0 = (int)(((nitem / p.ksplit) * CG + cta_rank) * BLOCK_M);
+            const int nm0 = (int)((decode_item(p, nitem).m_group * CG + cta_rank) * BLOCK_M);
             for (int kb = 0; kb < p.num_kblocks; ++kb) tma_prefetch_2d(&tmap_z, kb * BLOCK_K, nm0);
           }
           __syncwarp();
@@ -527,9 +561,8 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
       // descriptor constants: everything but the 14-bit start address
       const uint64_t desc_hi = smem_desc(0);
       for (int64_t item = first_item; item < p.n_items; item += item_stride) {
-        const int ks = (int)(item % p.ksplit);
-        const int t_begin = ks * p.tiles_per_split;
-        const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+        const Item it = decode_item(p, item);
+        const int t_begin = it.t_begin, t_end = it.t_end;
         for (int t = t_begin; t < t_end; ++t) {
           mbar_wait(bar_tm_empty + 8 * acc, acc_phase ^ 1);   // every epilogue warp has drained this accumulator
           tc_fence_after();
@@ -572,10 +605,9 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
     const int row_in_tile = quarter * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
     for (int64_t item = first_item; item < p.n_items; item += item_stride) {
-      const int64_t m_group = item / p.ksplit;
-      const int ks = (int)(item % p.ksplit);
-      const int t_begin = ks * p.tiles_per_split;
-      const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+      const Item it = decode_item(p, item);
+      const int64_t m_group = it.m_group;
+      const int t_begin = it.t_begin, t_end = it.t_end;
       const int64_t row = (m_group * CG + cta_rank) * BLOCK_M + row_in_tile;
       float* orow = p.out + row * p.ldc;
       for (int t = t_begin; t < t_end; ++t) {
@@ -631,10 +663,9 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
     const int row_in_tile = quarter * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
     for (int64_t item = first_item; item < p.n_items; item += item_stride) {
-      const int64_t m_group = item / p.ksplit;
-      const int ks = (int)(item % p.ksplit);
-      const int t_begin = ks * p.tiles_per_split;
-      const int t_end = min(p.n_tiles, t_begin + p.tiles_per_split);
+      const Item it = decode_item(p, item);
+      const int64_t m_group = it.m_group;
+      const int t_begin = it.t_begin, t_end = it.t_end;
       float bv = INFINITY;
       uint32_t bi = (uint32_t)(t_begin * BLOCK_N + half * 128);
       Top2 t2;
@@ -734,17 +765,21 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
           if (ov < sv || (ov == sv && oi < si)) { sv = ov; si = oi; }
         }
         const int64_t row = (m_group * CG + cta_rank) * BLOCK_M + row_in_tile;
+        const bool tail = TOP2 && it.tail_ks >= 0;
         if constexpr (TOP2) {
+          if (tail)                     // tail item: (best, runner-up) of this code range; merged by top2_merge_kernel
+            p.tail_rec[(int64_t)it.tail_ks * p.tail_rows + (row - p.tail_group0 * (CG * BLOCK_M))] =
+                make_uint4(__float_as_uint(bv), bi, __float_as_uint(sv), si);
           // runner-up index in the low word, the tf32 score gap (runner-up - winner; +inf when there is no runner-up,
           // NaN when the winner is a NaN) in the high word: the exact pass only re-evaluates pairs whose gap is within
           // the tf32 error bound of the row
-          if (row < p.N && p.idx2) {
+          if (!tail && row < p.N && p.idx2) {
             const uint32_t ri = (sv < INFINITY ? si : bi) + (uint32_t)p.k_offset;
             const float gap = (sv < INFINITY) ? (sv - bv) : ((bv == bv) ? INFINITY : bv);
             p.idx2[row] = (int64_t)(((unsigned long long)__float_as_uint(gap) << 32) | (unsigned long long)ri);
           }
         }
-        if (row < p.N) {
+        if (!tail && row < p.N) {
           const uint32_t gi = (uint32_t)(bi + p.k_offset);
           const long long key = pack_key(bv, gi);
           if (p.peers.n > 0) {
@@ -824,10 +859,40 @@ static int env_int(const char* name, int dflt) {
   return (e && e[0]) ? atoi(e) : dflt;
 }
 
+// Merges the tail items' code ranges (see Params): per row the best and the runner-up over all ranges, written exactly
+// as the search epilogue writes them (idx, and idx2 = runner-up column | tf32 score gap << 32).  Ranges are in increasing
+// code order, so on equal scores the earlier range holds the lower column; a NaN best is final (first NaN wins).
+__global__ void top2_merge_kernel(const uint4* __restrict__ rec, int splits, int64_t tail_rows, int64_t row0, int64_t N,
+                                  int64_t* __restrict__ idx, int64_t* __restrict__ idx2) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= tail_rows || row0 + r >= N) return;
+  uint4 c = rec[r];
+  float bv = __uint_as_float(c.x), sv = __uint_as_float(c.z);
+  uint32_t bi = c.y, si = c.w;
+  for (int s = 1; s < splits; ++s) {
+    c = rec[(int64_t)s * tail_rows + r];
+    const float cv = __uint_as_float(c.x), dv = __uint_as_float(c.z);
+    const uint32_t ci = c.y, di = c.w;
+    if (!(bv == bv)) break;                                  // NaN winner: nothing later can replace it
+    if (!(cv >= bv)) {                                       // strictly better, or the first NaN
+      // runner-up: the old winner, unless this range's own runner-up beats it (it cannot beat cv)
+      if (dv < bv) { sv = dv; si = di; } else { sv = bv; si = bi; }
+      bv = cv; bi = ci;
+    } else if (cv < sv) {                                    // ties keep the earlier (lower) column
+      sv = cv; si = ci;
+    }
+  }
+  const int64_t row = row0 + r;
+  const uint32_t ri = (sv < INFINITY) ? si : bi;
+  const float gap = (sv < INFINITY) ? (sv - bv) : ((bv == bv) ? INFINITY : bv);
+  idx2[row] = (int64_t)(((unsigned long long)__float_as_uint(gap) << 32) | (unsigned long long)ri);
+  idx[row] = (int64_t)bi;
+}
+
 template <int CG, int EPI>
 static int launch_cg(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t k_offset,
                      int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st, const PeerKeys* peers,
-                     int64_t* idx2, const float* e2max = nullptr) {
+                     int64_t* idx2, const float* e2max = nullptr, void* tail_rec = nullptr) {
   constexpr int B_STAGE_BYTES = (BLOCK_N / CG) * BLOCK_K * 4;
   Params p;
   p.N = N; p.K = K; p.k_offset = k_offset; p.D = D;
@@ -841,7 +906,34 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   if (m_groups < groups && EPI != EPI_TOP2) ksplit = (int)min_i64(p.n_tiles, (groups + m_groups - 1) / m_groups);
   p.tiles_per_split = (p.n_tiles + ksplit - 1) / ksplit;
   p.ksplit = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.n_items = m_groups * p.ksplit;
+  p.main_items = m_groups * p.ksplit;
+  p.tail_group0 = m_groups; p.tail_split = 1; p.tail_tiles = p.n_tiles; p.tail_rec = nullptr; p.tail_rows = 0;
+  // Who may split the tail: the top-2 search (records + merge kernel), and any search whose results are MIN-combined into
+  // packed keys anyway (caller-accumulated keys, the fused cross-GPU argmin of a sharded codebook) -- there a tail item
+  // simply issues the same atomics.  A search that writes idx directly keeps whole sweeps.
+  const bool tail_by_records = (EPI == EPI_TOP2) && tail_rec != nullptr;
+  const bool tail_by_atomics = (EPI == EPI_ARGMIN) && ksplit == 1 && (keys_accumulate || (peers && peers->n > 0));
+  if ((tail_by_records || tail_by_atomics) && env_int("KVQ_TF32_TAIL_SPLIT", 1) != 0) {
+    // the last round of the persistent grid holds r row groups for `groups` CTA groups: cut each into floor(groups / r)
+    // code ranges (at least TAIL_MIN_TILES code tiles each, so the per-item latent-tile load stays amortised)
+    const int64_t r = m_groups % groups;
+    if (r > 0) {
+      int split = (int)min_i64(groups / r, p.n_tiles / TAIL_MIN_TILES);
+      if (split >= 2) {
+        p.tail_tiles = (p.n_tiles + split - 1) / split;
+        p.tail_split = (p.n_tiles + p.tail_tiles - 1) / p.tail_tiles;
+        p.tail_group0 = m_groups - r;
+        p.main_items = p.tail_group0;                     // ksplit is 1 here
+        p.tail_rows = r * (int64_t)(CG * BLOCK_M);
+        if (tail_by_records) {
+          p.tail_rec = static_cast<uint4*>(tail_rec);
+          KVQ_REQUIRE((size_t)p.tail_split * (size_t)p.tail_rows * sizeof(uint4) <= TOP2_TAIL_REC_BYTES, KVQ_ERR_WORKSPACE,
+                      "tf32 top-2 search: tail records exceed their workspace block");
+        }
+      }
+    }
+  }
+  p.n_items = p.main_items + (m_groups - p.tail_group0) * p.tail_split;
   p.resident = (D <= RESIDENT_MAX_D) ? 1 : 0;
   const int a_bytes = p.resident ? p.num_kblocks * A_KBLOCK_BYTES : 0;
   const int stage_bytes = p.resident ? B_STAGE_BYTES : (A_KBLOCK_BYTES + B_STAGE_BYTES);
@@ -893,6 +985,12 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
     cfg.numAttrs = 1;
     count_launch();
     KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG, EPI>, mz, me, p));
+    if (p.tail_rec) {
+      count_launch();
+      top2_merge_kernel<<<(unsigned)((p.tail_rows + 255) / 256), 256, 0, st>>>(
+          p.tail_rec, p.tail_split, p.tail_rows, p.tail_group0 * (int64_t)(CG * BLOCK_M), N, idx, idx2);
+      KVQ_LAUNCH_CHECK();
+    }
   }
   // (also when the caller accumulates into its own key buffer: idx then reflects the merged keys, like the fp32 path)
   if (p.peers.n == 0 && p.use_atomic && idx) return launch_keys_to_idx(keys, N, idx, st);
@@ -916,6 +1014,7 @@ static int launch_store(const float* A, const float* B, int64_t M, int64_t Ncols
   p.tiles_per_split = (p.n_tiles + ksplit - 1) / ksplit;
   p.ksplit = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.n_items = m_groups * p.ksplit;
+  p.main_items = p.n_items; p.tail_group0 = m_groups; p.tail_split = 1; p.tail_tiles = p.n_tiles; p.tail_rec = nullptr; p.tail_rows = 0;
   p.resident = (Kc <= RESIDENT_MAX_D) ? 1 : 0;
   const int a_bytes = p.resident ? p.num_kblocks * A_KBLOCK_BYTES : 0;
   const int stage_bytes = p.resident ? B_STAGE_BYTES : (A_KBLOCK_BYTES + B_STAGE_BYTES);
@@ -1004,12 +1103,12 @@ bool tf32_refine_on_tensor_cores(int64_t N, int D, int64_t K) {
 }
 
 int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
-                            int64_t* idx, int64_t* idx2, cudaStream_t st, const float* e2max) {
+                            int64_t* idx, int64_t* idx2, cudaStream_t st, const float* e2max, void* tail_rec) {
   if (N <= 0) return KVQ_OK;
   KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (got D=%d)", D);
   KVQ_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)E & 15) == 0, KVQ_ERR_ARG,
               "tf32 search needs 16-byte aligned z and E (TMA)");
-  return t5::launch_cg<2, t5::EPI_TOP2>(z, E, e2, N, D, K, 0, idx, nullptr, 0, st, nullptr, idx2, e2max);
+  return t5::launch_cg<2, t5::EPI_TOP2>(z, E, e2, N, D, K, 0, idx, nullptr, 0, st, nullptr, idx2, e2max, tail_rec);
 }
 
 }  // namespace kvq

@@ -202,6 +202,35 @@ def test_keys_accumulate_across_codebook_shards():
         assert par.unexcused == 0 and par.raw_rate < 0.01
 
 
+def test_split_tail_round_of_the_tensor_core_search():
+    """More row groups than CTA pairs with a partly filled last round (20000 rows = 79 groups of 256 for 74 pairs): the
+    5 trailing groups are cut into code ranges -- merged from records by the top-2 search (default mode), by the key
+    atomics when keys are accumulated.  Results must equal the unsplit search's (KVQ_TF32_TAIL_SPLIT=0) row by row."""
+    import os
+    F = _kvq().functional
+    gen = torch.Generator().manual_seed(7)
+    N, D, K = 20000, 64, 8192
+    z = torch.randn(N, D, generator=gen); E = torch.randn(K, D, generator=gen)
+    zf, Ed = z.to(DEV), E.to(DEV)
+    out = {}
+    for split in ("1", "0"):
+        os.environ["KVQ_TF32_TAIL_SPLIT"] = split
+        try:
+            idx_auto = F.vq_forward(zf, Ed, 0.25, mode="auto")[3]
+            _, keys = F.search(zf, Ed[:5000].contiguous(), mode="tf32", want_idx=False, want_keys=True)
+            _, keys = F.search(zf, Ed[5000:].contiguous(), mode="tf32", k_offset=5000, want_idx=False, keys=keys,
+                               keys_accumulate=True, want_keys=True)
+            out[split] = (idx_auto.cpu(), F.keys_to_idx(keys).cpu())
+        finally:
+            os.environ.pop("KVQ_TF32_TAIL_SPLIT", None)
+    assert torch.equal(out["1"][0], out["0"][0])                  # default mode: exact pass on the same top-2 pairs
+    assert torch.equal(out["1"][1], out["0"][1])                  # plain tf32 keys: the same scores, the same minimum
+    rows = torch.arange(N - 2048, N)                              # the tail rows (and some before) against the oracle
+    ref = O.forward_fp32(z[rows], E, 0.25)
+    assert O.index_parity(out["1"][0][rows], ref.idx, z[rows], E).unexcused == 0
+    assert O.index_parity(out["1"][1][rows], ref.idx, z[rows], E).unexcused == 0
+
+
 def test_sharded_modules_world1_equal_plain_module():
     k = _kvq()
     z, E, gz = _seeded(4, 40, 64, 96, "normal")
