@@ -68,6 +68,7 @@ SIGNATURES = {
     "kvq_forward_backward_host_sharded": (c_int, [_P, _P, _P, c_float, c_int64, c_int, c_int64, c_float, c_int, c_int64,
                                                   _P, _P, _P, _P, _P, _P, c_int64]),
     "kvq_host_release": (c_int, []),
+    "kvq_search_plan": (c_int, [c_int64, c_int, c_int64, c_int, c_int, _P]),
 }
 
 _lib = None

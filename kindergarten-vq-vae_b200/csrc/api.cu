@@ -184,6 +184,12 @@ size_t kvq_workspace_bytes(int64_t N, int D, int64_t K) {
   return (w.bytes > b ? w.bytes : b) + 256;
 }
 
+int kvq_search_plan(int64_t N, int D, int64_t K, int kind, int sms, int64_t* out) {
+  int rc = check_shape("kvq_search_plan", N, D, K); if (rc) return rc;
+  KVQ_REQUIRE(N >= 1 && tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "kvq_search_plan: the tensor-core search needs N >= 1 and D %% 32 == 0");
+  return tf32_search_plan(N, K, kind, sms, out);
+}
+
 int kvq_code_norms(const float* E, int64_t K, int D, float* e2, int64_t K_pad, kvq_stream_t stream) {
   int rc = check_device(); if (rc) return rc;
   KVQ_REQUIRE(E && e2 && K_pad >= K, KVQ_ERR_ARG, "kvq_code_norms: null pointer or K_pad < K");

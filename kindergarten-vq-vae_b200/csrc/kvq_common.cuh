@@ -189,6 +189,7 @@ int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t 
                        int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st,
                        const PeerKeys* peers = nullptr);
 bool tf32_shape_ok(int64_t N, int D, int64_t K);
+int tf32_search_plan(int64_t N, int64_t K, int kind, int sms, int64_t* out10);   // kvq_search_plan
 bool tf32_refine_on_tensor_cores(int64_t N, int D, int64_t K);   // else the default mode uses the (exact) fp32 search
 bool tf32_operands_rounded();   // TMA rounds fp32 -> tf32 to nearest (default) instead of the MMA truncating
 int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,

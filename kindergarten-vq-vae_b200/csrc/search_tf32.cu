@@ -889,6 +889,44 @@ __global__ void top2_merge_kernel(const uint4* __restrict__ rec, int splits, int
   idx[row] = (int64_t)bi;
 }
 
+// How a search is cut into items for the persistent grid (pure host arithmetic; also behind kvq_search_plan, which the
+// CPU tests drive).  `groups` = CTA groups resident at once; `split_all` = the epilogue can combine code ranges of ANY row
+// group (plain argmin through packed keys); `split_tail` = it can combine the ranges of the trailing, partly filled round.
+struct ItemPlan {
+  int64_t m_groups, main_items, tail_group0, n_items, tail_rows;
+  int n_tiles, ksplit, tiles_per_split, tail_split, tail_tiles;
+};
+static ItemPlan plan_items(int64_t N, int64_t K, int cg, int groups, bool split_all, bool split_tail) {
+  ItemPlan q;
+  q.n_tiles = (int)((K + BLOCK_N - 1) / BLOCK_N);
+  const int64_t m_tiles = (N + BLOCK_M - 1) / BLOCK_M;
+  q.m_groups = (m_tiles + cg - 1) / cg;
+  int ksplit = 1;
+  // fewer row groups than CTA groups: split every group's code range so the GPU still fills
+  if (q.m_groups < groups && split_all) ksplit = (int)min_i64(q.n_tiles, (groups + q.m_groups - 1) / q.m_groups);
+  q.tiles_per_split = (q.n_tiles + ksplit - 1) / ksplit;
+  q.ksplit = (q.n_tiles + q.tiles_per_split - 1) / q.tiles_per_split;
+  q.main_items = q.m_groups * q.ksplit;
+  q.tail_group0 = q.m_groups; q.tail_split = 1; q.tail_tiles = q.n_tiles; q.tail_rows = 0;
+  if (split_tail && q.ksplit == 1) {
+    // the last round of the persistent grid holds r row groups for `groups` CTA groups: cut each into floor(groups / r)
+    // code ranges (at least TAIL_MIN_TILES code tiles each, so the per-item latent-tile load stays amortised)
+    const int64_t r = q.m_groups % groups;
+    if (r > 0) {
+      const int split = (int)min_i64(groups / r, q.n_tiles / TAIL_MIN_TILES);
+      if (split >= 2) {
+        q.tail_tiles = (q.n_tiles + split - 1) / split;
+        q.tail_split = (q.n_tiles + q.tail_tiles - 1) / q.tail_tiles;
+        q.tail_group0 = q.m_groups - r;
+        q.main_items = q.tail_group0;                     // ksplit is 1 here
+        q.tail_rows = r * (int64_t)(cg * BLOCK_M);
+      }
+    }
+  }
+  q.n_items = q.main_items + (q.m_groups - q.tail_group0) * q.tail_split;
+  return q;
+}
+
 template <int CG, int EPI>
 static int launch_cg(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K, int64_t k_offset,
                      int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st, const PeerKeys* peers,
@@ -897,43 +935,25 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   Params p;
   p.N = N; p.K = K; p.k_offset = k_offset; p.D = D;
   p.num_kblocks = D / BLOCK_K;
-  p.n_tiles = (int)((K + BLOCK_N - 1) / BLOCK_N);
-  const int64_t m_tiles = (N + BLOCK_M - 1) / BLOCK_M;
-  const int64_t m_groups = (m_tiles + CG - 1) / CG;
   const int groups = sm_count() / CG;                      // concurrently resident CTA groups
-  int ksplit = 1;
-  // (the top-2 epilogue keeps per-row state across the whole code range: never split it)
-  if (m_groups < groups && EPI != EPI_TOP2) ksplit = (int)min_i64(p.n_tiles, (groups + m_groups - 1) / m_groups);
-  p.tiles_per_split = (p.n_tiles + ksplit - 1) / ksplit;
-  p.ksplit = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.main_items = m_groups * p.ksplit;
-  p.tail_group0 = m_groups; p.tail_split = 1; p.tail_tiles = p.n_tiles; p.tail_rec = nullptr; p.tail_rows = 0;
-  // Who may split the tail: the top-2 search (records + merge kernel), and any search whose results are MIN-combined into
-  // packed keys anyway (caller-accumulated keys, the fused cross-GPU argmin of a sharded codebook) -- there a tail item
-  // simply issues the same atomics.  A search that writes idx directly keeps whole sweeps.
+  // Who may split what.  Every row group: the plain argmin (ranges MIN-combined through packed keys); never the top-2
+  // epilogue, which keeps per-row state across the whole code range.  The trailing round only: the top-2 search (records
+  // + merge kernel), and any plain search whose results are MIN-combined into packed keys anyway (caller-accumulated keys,
+  // the fused cross-GPU argmin of a sharded codebook) -- there a tail item simply issues the same atomics.  A search that
+  // writes idx directly keeps whole sweeps.
   const bool tail_by_records = (EPI == EPI_TOP2) && tail_rec != nullptr;
-  const bool tail_by_atomics = (EPI == EPI_ARGMIN) && ksplit == 1 && (keys_accumulate || (peers && peers->n > 0));
-  if ((tail_by_records || tail_by_atomics) && env_int("KVQ_TF32_TAIL_SPLIT", 1) != 0) {
-    // the last round of the persistent grid holds r row groups for `groups` CTA groups: cut each into floor(groups / r)
-    // code ranges (at least TAIL_MIN_TILES code tiles each, so the per-item latent-tile load stays amortised)
-    const int64_t r = m_groups % groups;
-    if (r > 0) {
-      int split = (int)min_i64(groups / r, p.n_tiles / TAIL_MIN_TILES);
-      if (split >= 2) {
-        p.tail_tiles = (p.n_tiles + split - 1) / split;
-        p.tail_split = (p.n_tiles + p.tail_tiles - 1) / p.tail_tiles;
-        p.tail_group0 = m_groups - r;
-        p.main_items = p.tail_group0;                     // ksplit is 1 here
-        p.tail_rows = r * (int64_t)(CG * BLOCK_M);
-        if (tail_by_records) {
-          p.tail_rec = static_cast<uint4*>(tail_rec);
-          KVQ_REQUIRE((size_t)p.tail_split * (size_t)p.tail_rows * sizeof(uint4) <= TOP2_TAIL_REC_BYTES, KVQ_ERR_WORKSPACE,
-                      "tf32 top-2 search: tail records exceed their workspace block");
-        }
-      }
-    }
+  const bool tail_by_atomics = (EPI == EPI_ARGMIN) && (keys_accumulate || (peers && peers->n > 0));
+  const ItemPlan q = plan_items(N, K, CG, groups, /*split_all=*/EPI != EPI_TOP2,
+                                (tail_by_records || tail_by_atomics) && env_int("KVQ_TF32_TAIL_SPLIT", 1) != 0);
+  p.n_tiles = q.n_tiles; p.ksplit = q.ksplit; p.tiles_per_split = q.tiles_per_split;
+  p.main_items = q.main_items; p.tail_group0 = q.tail_group0; p.tail_split = q.tail_split; p.tail_tiles = q.tail_tiles;
+  p.tail_rows = q.tail_rows; p.n_items = q.n_items;
+  p.tail_rec = nullptr;
+  if (tail_by_records && q.tail_split > 1) {
+    p.tail_rec = static_cast<uint4*>(tail_rec);
+    KVQ_REQUIRE((size_t)p.tail_split * (size_t)p.tail_rows * sizeof(uint4) <= TOP2_TAIL_REC_BYTES, KVQ_ERR_WORKSPACE,
+                "tf32 top-2 search: tail records exceed their workspace block");
   }
-  p.n_items = p.main_items + (m_groups - p.tail_group0) * p.tail_split;
   p.resident = (D <= RESIDENT_MAX_D) ? 1 : 0;
   const int a_bytes = p.resident ? p.num_kblocks * A_KBLOCK_BYTES : 0;
   const int stage_bytes = p.resident ? B_STAGE_BYTES : (A_KBLOCK_BYTES + B_STAGE_BYTES);
@@ -1100,6 +1120,16 @@ bool tf32_refine_on_tensor_cores(int64_t N, int D, int64_t K) {
   const double t_tensor = waves * n_tiles * (double)(D / t5::BLOCK_K) * 0.30e-6;   // 4 MMAs x 128 cycles per k-block
   const double t_fp32 = 2.0 * (double)N * (double)K * (double)D / 30e12;           // measured 30-39 TFLOP/s
   return t_tensor < t_fp32;
+}
+
+int tf32_search_plan(int64_t N, int64_t K, int kind, int sms, int64_t* out) {
+  const int groups = (sms > 0 ? sms : sm_count()) / 2;
+  KVQ_REQUIRE(groups >= 1 && kind >= 0 && kind <= 2 && out, KVQ_ERR_ARG, "kvq_search_plan: bad arguments");
+  const t5::ItemPlan q = t5::plan_items(N, K, 2, groups, /*split_all=*/kind != 1, /*split_tail=*/kind != 0);
+  const int64_t v[10] = {q.m_groups, q.n_tiles, q.ksplit, q.tiles_per_split, q.main_items, q.tail_group0, q.tail_split,
+                         q.tail_tiles, q.tail_rows, q.n_items};
+  for (int i = 0; i < 10; ++i) out[i] = v[i];
+  return KVQ_OK;
 }
 
 int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,

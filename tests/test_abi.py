@@ -146,3 +146,71 @@ def test_pack_key_order_property(lib):
         assert k1 & 0xFFFFFFFF == i1
 
     check()
+
+
+def _plan(lib, N, K, kind, sms=148, D=256):
+    out = (ctypes.c_int64 * 10)()
+    rc = lib.kvq_search_plan(N, D, K, kind, sms, out)
+    assert rc == 0, lib.kvq_last_error()
+    names = ("row_groups", "code_tiles", "ksplit", "tiles_per_split", "main_items", "tail_group0", "tail_split",
+             "tail_tiles", "tail_rows", "n_items")
+    return dict(zip(names, [int(v) for v in out]))
+
+
+def test_search_plan_known_cases(lib):
+    """Host arithmetic of the tensor-core search's item decomposition (no device needed)."""
+    # headline shape, default mode: 4096 row groups = 55 full rounds of 74 CTA pairs + 26 groups cut into 2 code ranges
+    p = _plan(lib, 1 << 20, 65536, kind=1)
+    assert (p["row_groups"], p["code_tiles"], p["ksplit"]) == (4096, 256, 1)
+    assert (p["main_items"], p["tail_group0"], p["tail_split"], p["tail_tiles"]) == (4070, 4070, 2, 128)
+    assert p["tail_rows"] == 26 * 256 and p["n_items"] == 4070 + 52
+    # the host pipeline's 4096-row lead-in chunk: 16 groups, each cut into 4 ranges of 64 code tiles
+    p = _plan(lib, 4096, 65536, kind=1)
+    assert (p["main_items"], p["tail_group0"], p["tail_split"], p["tail_tiles"], p["n_items"]) == (0, 0, 4, 64, 64)
+    # one full wave: nothing to split
+    p = _plan(lib, 74 * 256, 65536, kind=1)
+    assert p["tail_split"] == 1 and p["n_items"] == 74
+    # the reference's own shape: 2 code tiles cannot be cut (8 tiles per range at least), top-2 search stays unsplit
+    p = _plan(lib, 4096, 512, kind=1, D=768)
+    assert (p["ksplit"], p["tail_split"], p["n_items"]) == (1, 1, 16)
+    # plain argmin writing idx directly: few rows facing a large codebook split EVERY group's code range, never the tail
+    p = _plan(lib, 200, 16384, kind=0)
+    assert p["row_groups"] == 1 and p["ksplit"] == 64 and p["tail_split"] == 1 and p["n_items"] == 64
+    p = _plan(lib, 1 << 20, 65536, kind=0)
+    assert p["ksplit"] == 1 and p["tail_split"] == 1 and p["n_items"] == 4096
+    # key-combining plain search (sharded codebook, 131072 codes per rank): the tail splits like the top-2 search's
+    p = _plan(lib, 1 << 20, 131072, kind=2)
+    assert (p["tail_group0"], p["tail_split"], p["tail_tiles"]) == (4070, 2, 256)
+    assert lib.kvq_search_plan(100, 36, 512, 1, 148, (ctypes.c_int64 * 10)()) != 0        # D % 32 != 0: not this kernel
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_search_plan_invariants(lib, kind):
+    """Every code tile of every row group is covered exactly once, no item is empty, the split tail fits one round of the
+    grid and its records fit their workspace block."""
+    import random
+    rng = random.Random(1234 + kind)
+    for _ in range(400):
+        sms = rng.choice([148, 148, 132, 64, 2])
+        groups = sms // 2
+        N = rng.choice([1, 200, 4096, 18944, 20000, 1 << 20, rng.randrange(1, 3_000_000)])
+        K = rng.choice([1, 300, 512, 8192, 65536, 140000, rng.randrange(1, 1_200_000)])
+        p = _plan(lib, N, K, kind, sms=sms)
+        assert p["row_groups"] == -(-N // 256) and p["code_tiles"] == -(-K // 256)
+        # main items: ksplit ranges of tiles_per_split tiles cover the tiles, the last range is not empty
+        assert p["ksplit"] * p["tiles_per_split"] >= p["code_tiles"] > (p["ksplit"] - 1) * p["tiles_per_split"]
+        assert p["main_items"] == p["tail_group0"] * p["ksplit"]
+        tail_groups = p["row_groups"] - p["tail_group0"]
+        assert p["n_items"] == p["main_items"] + tail_groups * p["tail_split"]
+        assert p["tail_rows"] == (tail_groups * 256 if p["tail_split"] > 1 else 0)
+        if kind == 1:
+            assert p["ksplit"] == 1                          # the top-2 epilogue never splits a whole sweep
+        if kind == 0:
+            assert p["tail_split"] == 1 and tail_groups == 0
+        if p["tail_split"] > 1:
+            assert p["ksplit"] == 1 and 0 < tail_groups < groups and p["tail_group0"] % groups == 0
+            assert p["tail_split"] * p["tail_tiles"] >= p["code_tiles"] > (p["tail_split"] - 1) * p["tail_tiles"]
+            assert p["tail_tiles"] >= 8 and tail_groups * p["tail_split"] <= groups
+            assert p["tail_split"] * p["tail_rows"] * 16 <= 128 * 256 * 16       # TOP2_TAIL_REC_BYTES
+        else:
+            assert tail_groups == 0
