@@ -121,6 +121,41 @@ def test_headline_shape_against_the_oracle():
     assert bool((dE[hist == 0] == 0).all())
 
 
+def test_headline_shape_size_independent_properties():
+    """N = 2^20, D = 256, K = 65536, default search -- properties that need no oracle:
+      * idempotence: quantising the quantised latents (exact codebook rows) returns the same codes, residual exactly 0;
+      * row independence: a row's result does not depend on where it sits (permuting the rows permutes the results bitwise:
+        tile position, wave, the split tail round and the merge kernel must all be invisible);
+      * linearity of the codebook gradient in the loss weight (power-of-two scaling is exact in floating point);
+      * a checksum: the column sums of dE equal beta * 2 / (N D) * sum_i (E[idx_i] - z_i)."""
+    F = _kvq().functional
+    N, D, K, beta = 1 << 20, 256, 65536, 0.25
+    z, gz, E = _headline_inputs(N, D, K)
+    del gz
+    loss, z_q, perp, idx, hist = F.vq_forward(z, E, beta, mode="auto")
+    # idempotence (rows of a random codebook are distinct, so the nearest code of E[k] is k at distance exactly 0)
+    q = E[idx]
+    loss_q, z_qq, perp_q, idx_q, hist_q = F.vq_forward(q, E, beta, mode="auto")
+    assert torch.equal(idx_q, idx) and torch.equal(z_qq, q) and float(loss_q) == 0.0
+    assert torch.equal(hist_q, hist) and abs(float(perp_q) - float(perp)) <= 1e-6 * float(perp)
+    del z_qq, q
+    # row independence
+    perm = torch.randperm(N, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    zp = z[perm].contiguous()
+    loss_p, z_qp, perp_p, idx_p, hist_p = F.vq_forward(zp, E, beta, mode="auto")
+    assert torch.equal(idx_p, idx[perm]) and torch.equal(z_qp, z_q[perm]) and torch.equal(hist_p, hist)
+    assert abs(float(loss_p) - float(loss)) <= 1e-6 * float(loss)          # summation order differs
+    del zp, z_qp, idx_p
+    # linearity of dE in the loss weight, and its checksum
+    one, two = torch.tensor(1.0, device=DEV), torch.tensor(2.0, device=DEV)
+    _, dE1 = F.vq_backward(z, E, idx, hist, beta, g_loss=one, need_dz=False)
+    _, dE2 = F.vq_backward(z, E, idx, hist, beta, g_loss=two, need_dz=False)
+    assert torch.equal(dE2, 2.0 * dE1)
+    want = (E[idx].double().sum(0) - z.double().sum(0)) * (2.0 * beta / (N * D))
+    got = dE1.double().sum(0)
+    assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max()) + 1e-12
+
+
 @pytest.mark.parametrize("shape", [(1 << 20, 256, 65536, "normal"), (1 << 20, 256, 4096, "collapsed"),
                                    (100000, 128, 1000, "skewed"), (4096, 768, 512, "normal"), (77, 32, 5, "normal")])
 def test_codebook_gradient_is_bitwise_reproducible(shape):
