@@ -74,9 +74,8 @@ int kvq_device_info(int* sm_count, int* cc_major, int* cc_minor);
 size_t kvq_workspace_bytes(int64_t N, int D, int64_t K);
 
 /* How the tensor-core search cuts an N x K problem into items for its persistent grid -- pure host arithmetic, no device
- * needed (tests, diagnostics).  kind: 0 = plain argmin writing idx directly, 1 = top-2 search (the default mode),
- * 2 = plain argmin whose results are MIN-combined into packed keys (accumulated keys, cross-GPU argmin).
- * sms: SM count to plan for (<= 0: the current device's).  out receives 10 values:
+ * needed (tests, diagnostics).  kind: 0 = plain argmin (search mode "tf32", sharded searches), 1 = top-2 search (the
+ * default mode).  sms: SM count to plan for (<= 0: the current device's).  out receives 10 values:
  *   { row_groups, code_tiles, ksplit, tiles_per_split, main_items, tail_group0, tail_split, tail_tiles, tail_rows, n_items }
  * Items [0, main_items) sweep tiles_per_split code tiles of row group item / ksplit; the remaining items cut the row
  * groups [tail_group0, row_groups) -- the partly filled last round of the grid -- into tail_split ranges of tail_tiles

@@ -119,7 +119,7 @@ static int resolve_mode(int mode, int64_t N, int D, int64_t K, int* out, bool al
 int run_search(int mode, const float* z, const float* E, const float* e2, const float* e2max, int64_t N, int D, int64_t K,
                int64_t* idx, long long* scratch, cudaStream_t st, int* deferred, void* tail_rec) {
   if (deferred) *deferred = 0;
-  if (mode == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, e2, N, D, K, 0, idx, scratch, 0, st);
+  if (mode == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, e2, N, D, K, 0, idx, scratch, 0, st, nullptr, tail_rec);
   if (mode == KVQ_SEARCH_TF32_REFINE && tf32_refine_on_tensor_cores(N, D, K)) {
     // tensor-core search keeping the two best codes per latent, then an exact float64 re-evaluation of the pair
     int64_t* runner_up = reinterpret_cast<int64_t*>(scratch);
@@ -217,7 +217,7 @@ int kvq_search(const float* z, const float* E, int64_t N, int D, int64_t K, int6
                 "kvq_search: tf32_refine is for unsharded searches that return indices (no keys, k_offset 0)");
     return run_search(m, z, E, w.e2, w.e2max, N, D, K, idx, w.keys, st, nullptr, w.tail_rec);
   }
-  if (m == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
+  if (m == KVQ_SEARCH_TF32) return launch_search_tf32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st, nullptr, w.tail_rec);
   return launch_search_fp32(z, E, w.e2, N, D, K, k_offset, idx, kbuf, keys_accumulate, st);
 }
 

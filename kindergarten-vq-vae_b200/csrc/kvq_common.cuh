@@ -187,7 +187,7 @@ int launch_search_fp32(const float* z, const float* E, const float* e2, int64_t 
                        const PeerKeys* peers = nullptr);
 int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
                        int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st,
-                       const PeerKeys* peers = nullptr);
+                       const PeerKeys* peers = nullptr, void* tail_rec = nullptr);
 bool tf32_shape_ok(int64_t N, int D, int64_t K);
 int tf32_search_plan(int64_t N, int64_t K, int kind, int sms, int64_t* out10);   // kvq_search_plan
 bool tf32_refine_on_tensor_cores(int64_t N, int D, int64_t K);   // else the default mode uses the (exact) fp32 search

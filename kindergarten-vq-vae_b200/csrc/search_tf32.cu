@@ -765,11 +765,13 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
           if (ov < sv || (ov == sv && oi < si)) { sv = ov; si = oi; }
         }
         const int64_t row = (m_group * CG + cta_rank) * BLOCK_M + row_in_tile;
-        const bool tail = TOP2 && it.tail_ks >= 0;
+        // tail item of a search that cannot MIN-combine through keys: (best, runner-up) of this code range goes to a
+        // record; tail_merge_kernel combines the ranges (plain argmin: no runner-up, sv = +inf)
+        const bool tail = it.tail_ks >= 0 && p.tail_rec != nullptr;
+        if (tail)
+          p.tail_rec[(int64_t)it.tail_ks * p.tail_rows + (row - p.tail_group0 * (CG * BLOCK_M))] =
+              make_uint4(__float_as_uint(bv), bi, __float_as_uint(sv), si);
         if constexpr (TOP2) {
-          if (tail)                     // tail item: (best, runner-up) of this code range; merged by top2_merge_kernel
-            p.tail_rec[(int64_t)it.tail_ks * p.tail_rows + (row - p.tail_group0 * (CG * BLOCK_M))] =
-                make_uint4(__float_as_uint(bv), bi, __float_as_uint(sv), si);
           // runner-up index in the low word, the tf32 score gap (runner-up - winner; +inf when there is no runner-up,
           // NaN when the winner is a NaN) in the high word: the exact pass only re-evaluates pairs whose gap is within
           // the tf32 error bound of the row
@@ -860,10 +862,12 @@ static int env_int(const char* name, int dflt) {
 }
 
 // Merges the tail items' code ranges (see Params): per row the best and the runner-up over all ranges, written exactly
-// as the search epilogue writes them (idx, and idx2 = runner-up column | tf32 score gap << 32).  Ranges are in increasing
-// code order, so on equal scores the earlier range holds the lower column; a NaN best is final (first NaN wins).
-__global__ void top2_merge_kernel(const uint4* __restrict__ rec, int splits, int64_t tail_rows, int64_t row0, int64_t N,
-                                  int64_t* __restrict__ idx, int64_t* __restrict__ idx2) {
+// as the search epilogue writes them (idx and / or the packed key; for the top-2 search also idx2 = runner-up column |
+// tf32 score gap << 32).  Ranges are in increasing code order, so on equal scores the earlier range holds the lower
+// column; a NaN best is final (first NaN wins).
+__global__ void tail_merge_kernel(const uint4* __restrict__ rec, int splits, int64_t tail_rows, int64_t row0, int64_t N,
+                                  int64_t k_offset, int64_t* __restrict__ idx, int64_t* __restrict__ idx2,
+                                  long long* __restrict__ keys) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= tail_rows || row0 + r >= N) return;
   uint4 c = rec[r];
@@ -883,10 +887,14 @@ __global__ void top2_merge_kernel(const uint4* __restrict__ rec, int splits, int
     }
   }
   const int64_t row = row0 + r;
-  const uint32_t ri = (sv < INFINITY) ? si : bi;
-  const float gap = (sv < INFINITY) ? (sv - bv) : ((bv == bv) ? INFINITY : bv);
-  idx2[row] = (int64_t)(((unsigned long long)__float_as_uint(gap) << 32) | (unsigned long long)ri);
-  idx[row] = (int64_t)bi;
+  const uint32_t gi = bi + (uint32_t)k_offset;
+  if (idx2) {
+    const uint32_t ri = ((sv < INFINITY) ? si : bi) + (uint32_t)k_offset;
+    const float gap = (sv < INFINITY) ? (sv - bv) : ((bv == bv) ? INFINITY : bv);
+    idx2[row] = (int64_t)(((unsigned long long)__float_as_uint(gap) << 32) | (unsigned long long)ri);
+  }
+  if (idx) idx[row] = (int64_t)gi;
+  if (keys) keys[row] = pack_key(bv, gi);
 }
 
 // How a search is cut into items for the persistent grid (pure host arithmetic; also behind kvq_search_plan, which the
@@ -937,12 +945,13 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   p.num_kblocks = D / BLOCK_K;
   const int groups = sm_count() / CG;                      // concurrently resident CTA groups
   // Who may split what.  Every row group: the plain argmin (ranges MIN-combined through packed keys); never the top-2
-  // epilogue, which keeps per-row state across the whole code range.  The trailing round only: the top-2 search (records
-  // + merge kernel), and any plain search whose results are MIN-combined into packed keys anyway (caller-accumulated keys,
-  // the fused cross-GPU argmin of a sharded codebook) -- there a tail item simply issues the same atomics.  A search that
-  // writes idx directly keeps whole sweeps.
-  const bool tail_by_records = (EPI == EPI_TOP2) && tail_rec != nullptr;
-  const bool tail_by_atomics = (EPI == EPI_ARGMIN) && (keys_accumulate || (peers && peers->n > 0));
+  // epilogue, which keeps per-row state across the whole code range.  The trailing round only: through records + the merge
+  // kernel (top-2 search, plain search writing idx / keys directly; needs the caller's record block), or, where results are
+  // MIN-combined into packed keys anyway (caller-accumulated keys, the fused cross-GPU argmin of a sharded codebook), by
+  // simply issuing the same atomics.
+  const bool combines = keys_accumulate || (peers && peers->n > 0);
+  const bool tail_by_records = tail_rec != nullptr && (EPI == EPI_TOP2 || (EPI == EPI_ARGMIN && !combines));
+  const bool tail_by_atomics = (EPI == EPI_ARGMIN) && combines;
   const ItemPlan q = plan_items(N, K, CG, groups, /*split_all=*/EPI != EPI_TOP2,
                                 (tail_by_records || tail_by_atomics) && env_int("KVQ_TF32_TAIL_SPLIT", 1) != 0);
   p.n_tiles = q.n_tiles; p.ksplit = q.ksplit; p.tiles_per_split = q.tiles_per_split;
@@ -1007,8 +1016,8 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
     KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG, EPI>, mz, me, p));
     if (p.tail_rec) {
       count_launch();
-      top2_merge_kernel<<<(unsigned)((p.tail_rows + 255) / 256), 256, 0, st>>>(
-          p.tail_rec, p.tail_split, p.tail_rows, p.tail_group0 * (int64_t)(CG * BLOCK_M), N, idx, idx2);
+      tail_merge_kernel<<<(unsigned)((p.tail_rows + 255) / 256), 256, 0, st>>>(
+          p.tail_rec, p.tail_split, p.tail_rows, p.tail_group0 * (int64_t)(CG * BLOCK_M), N, k_offset, idx, idx2, keys);
       KVQ_LAUNCH_CHECK();
     }
   }
@@ -1094,7 +1103,7 @@ bool tf32_shape_ok(int64_t N, int D, int64_t K) {
 
 int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
                        int64_t k_offset, int64_t* idx, long long* keys, int keys_accumulate, cudaStream_t st,
-                       const PeerKeys* peers) {
+                       const PeerKeys* peers, void* tail_rec) {
   if (N <= 0) return KVQ_OK;
   KVQ_REQUIRE(tf32_shape_ok(N, D, K), KVQ_ERR_SHAPE, "tf32 search needs D %% 32 == 0 (got N=%lld D=%d K=%lld)",
               (long long)N, D, (long long)K);
@@ -1102,7 +1111,8 @@ int launch_search_tf32(const float* z, const float* E, const float* e2, int64_t 
               "tf32 search needs 16-byte aligned z and E (TMA)");
   static const int cta_group = t5::env_int("KVQ_TF32_CTA_GROUP", 2);
   if (cta_group == 1) return t5::launch_cg<1, t5::EPI_ARGMIN>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers, nullptr);
-  return t5::launch_cg<2, t5::EPI_ARGMIN>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers, nullptr);
+  return t5::launch_cg<2, t5::EPI_ARGMIN>(z, E, e2, N, D, K, k_offset, idx, keys, keys_accumulate, st, peers, nullptr,
+                                          nullptr, tail_rec);
 }
 
 // Does the default mode (tensor-core top-2 search + exact re-evaluation) run on the tensor cores for this shape?
@@ -1124,8 +1134,8 @@ bool tf32_refine_on_tensor_cores(int64_t N, int D, int64_t K) {
 
 int tf32_search_plan(int64_t N, int64_t K, int kind, int sms, int64_t* out) {
   const int groups = (sms > 0 ? sms : sm_count()) / 2;
-  KVQ_REQUIRE(groups >= 1 && kind >= 0 && kind <= 2 && out, KVQ_ERR_ARG, "kvq_search_plan: bad arguments");
-  const t5::ItemPlan q = t5::plan_items(N, K, 2, groups, /*split_all=*/kind != 1, /*split_tail=*/kind != 0);
+  KVQ_REQUIRE(groups >= 1 && kind >= 0 && kind <= 1 && out, KVQ_ERR_ARG, "kvq_search_plan: bad arguments");
+  const t5::ItemPlan q = t5::plan_items(N, K, 2, groups, /*split_all=*/kind == 0, /*split_tail=*/true);
   const int64_t v[10] = {q.m_groups, q.n_tiles, q.ksplit, q.tiles_per_split, q.main_items, q.tail_group0, q.tail_split,
                          q.tail_tiles, q.tail_rows, q.n_items};
   for (int i = 0; i < 10; ++i) out[i] = v[i];

@@ -173,18 +173,16 @@ def test_search_plan_known_cases(lib):
     # the reference's own shape: 2 code tiles cannot be cut (8 tiles per range at least), top-2 search stays unsplit
     p = _plan(lib, 4096, 512, kind=1, D=768)
     assert (p["ksplit"], p["tail_split"], p["n_items"]) == (1, 1, 16)
-    # plain argmin writing idx directly: few rows facing a large codebook split EVERY group's code range, never the tail
+    # plain argmin: few rows facing a large codebook split EVERY group's code range (merged through packed keys) ...
     p = _plan(lib, 200, 16384, kind=0)
     assert p["row_groups"] == 1 and p["ksplit"] == 64 and p["tail_split"] == 1 and p["n_items"] == 64
-    p = _plan(lib, 1 << 20, 65536, kind=0)
-    assert p["ksplit"] == 1 and p["tail_split"] == 1 and p["n_items"] == 4096
-    # key-combining plain search (sharded codebook, 131072 codes per rank): the tail splits like the top-2 search's
-    p = _plan(lib, 1 << 20, 131072, kind=2)
-    assert (p["tail_group0"], p["tail_split"], p["tail_tiles"]) == (4070, 2, 256)
+    # ... and many rows split the tail round like the top-2 search (sharded codebook, 131072 codes per rank)
+    p = _plan(lib, 1 << 20, 131072, kind=0)
+    assert (p["ksplit"], p["tail_group0"], p["tail_split"], p["tail_tiles"]) == (1, 4070, 2, 256)
     assert lib.kvq_search_plan(100, 36, 512, 1, 148, (ctypes.c_int64 * 10)()) != 0        # D % 32 != 0: not this kernel
 
 
-@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("kind", [0, 1])
 def test_search_plan_invariants(lib, kind):
     """Every code tile of every row group is covered exactly once, no item is empty, the split tail fits one round of the
     grid and its records fit their workspace block."""
@@ -205,8 +203,6 @@ def test_search_plan_invariants(lib, kind):
         assert p["tail_rows"] == (tail_groups * 256 if p["tail_split"] > 1 else 0)
         if kind == 1:
             assert p["ksplit"] == 1                          # the top-2 epilogue never splits a whole sweep
-        if kind == 0:
-            assert p["tail_split"] == 1 and tail_groups == 0
         if p["tail_split"] > 1:
             assert p["ksplit"] == 1 and 0 < tail_groups < groups and p["tail_group0"] % groups == 0
             assert p["tail_split"] * p["tail_tiles"] >= p["code_tiles"] > (p["tail_split"] - 1) * p["tail_tiles"]

@@ -204,8 +204,8 @@ def test_keys_accumulate_across_codebook_shards():
 
 def test_split_tail_round_of_the_tensor_core_search():
     """More row groups than CTA pairs with a partly filled last round (20000 rows = 79 groups of 256 for 74 pairs): the
-    5 trailing groups are cut into code ranges -- merged from records by the top-2 search (default mode), by the key
-    atomics when keys are accumulated.  Results must equal the unsplit search's (KVQ_TF32_TAIL_SPLIT=0) row by row."""
+    5 trailing groups are cut into code ranges -- merged from records by the top-2 search (default mode) and by the plain
+    search that writes idx directly, by the key atomics when keys are accumulated.  Results must equal the unsplit search's (KVQ_TF32_TAIL_SPLIT=0) row by row."""
     import os
     F = _kvq().functional
     gen = torch.Generator().manual_seed(7)
@@ -220,11 +220,13 @@ def test_split_tail_round_of_the_tensor_core_search():
             _, keys = F.search(zf, Ed[:5000].contiguous(), mode="tf32", want_idx=False, want_keys=True)
             _, keys = F.search(zf, Ed[5000:].contiguous(), mode="tf32", k_offset=5000, want_idx=False, keys=keys,
                                keys_accumulate=True, want_keys=True)
-            out[split] = (idx_auto.cpu(), F.keys_to_idx(keys).cpu())
+            idx_plain, _ = F.search(zf, Ed, mode="tf32")              # plain search writing idx directly: records too
+            out[split] = (idx_auto.cpu(), F.keys_to_idx(keys).cpu(), idx_plain.cpu())
         finally:
             os.environ.pop("KVQ_TF32_TAIL_SPLIT", None)
     assert torch.equal(out["1"][0], out["0"][0])                  # default mode: exact pass on the same top-2 pairs
     assert torch.equal(out["1"][1], out["0"][1])                  # plain tf32 keys: the same scores, the same minimum
+    assert torch.equal(out["1"][2], out["0"][2])
     rows = torch.arange(N - 2048, N)                              # the tail rows (and some before) against the oracle
     ref = O.forward_fp32(z[rows], E, 0.25)
     assert O.index_parity(out["1"][0][rows], ref.idx, z[rows], E).unexcused == 0
