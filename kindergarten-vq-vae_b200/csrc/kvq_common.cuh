@@ -195,7 +195,7 @@ bool tf32_operands_rounded();   // TMA rounds fp32 -> tf32 to nearest (default) 
 int launch_search_tf32_top2(const float* z, const float* E, const float* e2, int64_t N, int D, int64_t K,
                             int64_t* idx, int64_t* idx2, cudaStream_t st, const float* e2max = nullptr,
                             void* tail_rec = nullptr);
-// workspace block of the top-2 search's tail items (see search_tf32.cu: Params): 16 bytes per row and code range, at most
+// workspace block of the tensor-core search's tail items (see search_tf32.cu: Params): 16 bytes per row and code range, at most
 // one persistent round of rows (SMs / 2 groups of 256) -- sized for 256 SMs
 constexpr size_t TOP2_TAIL_REC_BYTES = (size_t)128 * 256 * 16;
 int launch_refine_top2(const float* z, const float* E, int64_t N, int D, int64_t* idx, const int64_t* idx2,

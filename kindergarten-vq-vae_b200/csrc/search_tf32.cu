@@ -71,10 +71,11 @@ struct Params {
   int tiles_per_split;  // code tiles per item
   int ksplit;
   int64_t n_items;      // main_items + tail items
-  // Items [0, main_items) sweep `tiles_per_split` code tiles of row group item / ksplit.  Items beyond that are the TAIL
-  // (top-2 search only): the row groups of the last, partly filled round of the persistent grid, each cut into tail_split
-  // code ranges so that the round takes 1 / tail_split of a sweep instead of a whole one with most SMs idle.  A tail item
-  // leaves (best, runner-up) of its code range in tail_rec; a small kernel merges the ranges afterwards.
+  // Items [0, main_items) sweep `tiles_per_split` code tiles of row group item / ksplit.  Items beyond that are the TAIL:
+  // the row groups of the last, partly filled round of the persistent grid, each cut into tail_split code ranges so that
+  // the round takes 1 / tail_split of a sweep instead of a whole one with most SMs idle.  With tail_rec a tail item leaves
+  // (best, runner-up) of its code range in a record and a small kernel merges the ranges afterwards; without it the
+  // item MIN-combines its packed key like any other (searches that combine through keys anyway).
   int64_t main_items;
   int64_t tail_group0;  // first row group of the tail
   int tail_split, tail_tiles;
