@@ -364,10 +364,10 @@ def run_kvq(args):
     dE_timed = vq.embedding.weight.grad.detach().clone()
 
     # ---- end to end with host buffers (H2D + compute + D2H inside the timed region) --------------------
-    # Measured right after the headline, before the checks and side measurements below.  The call is copy-bound only while
-    # the chunked search keeps up with PCIe (0.80 ms of search against 0.82 ms of copies per one-wave chunk), so it is
-    # sensitive to the state the earlier phases leave the box in: the same call took 48.2 ms here and 51.6 ms after the
-    # CPU oracle check and the interleaved A/B block of the same process (gpurun_out b1 / b2, round 2).
+    # Measured right after the headline.  The call is bound by the box's host <-> device copy path, which varies between
+    # boxes and between moments on one box (traced calls, tools/e2e_trace_stats.py: the inbound copies alone end after
+    # 46 ms on one box and after 54 ms on another, with compute never more than 0.5 ms behind them), so the bare-copy
+    # ceiling is measured directly after it.
     e2e = None
     if not args.no_e2e:
         e2e = measure_e2e(torch, dist, F, vq, z, gz, E, dev, world, args)
