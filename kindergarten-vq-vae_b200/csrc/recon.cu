@@ -10,7 +10,8 @@
 //     loss = sum_r (lse_r - x_r[id_r]) / R;   matches per sentence and in total for seq_acc (common/metrics.py:8-36)
 // and the backward is one more pass:  dlogits = g * (exp(x - lse_r) - [j == id_r]) / R.
 //
-// One block per row (a row of 30522 logits is 122 KB); coalesced scalar loads, four in flight per thread.
+// One block per row (a row of 30522 logits is 122 KB); coalesced 8-byte loads, four in flight per thread, eight logits
+// per online-softmax update.
 // HBM bytes: forward 4*R*V read; backward 4*R*V read + 4*R*V write.
 #include "kvq_common.cuh"
 
@@ -47,6 +48,39 @@ __device__ __forceinline__ RowStat stat_merge(const RowStat& a, const RowStat& b
   return r;
 }
 
+// Eight logits at a time: one maximum, at most one rescale of the running sum, eight exponentials -- instead of a
+// data-dependent branch per element -- and the arg-max looks inside a group only when the group's maximum beats the
+// running one (after the first few groups: almost never).  A NaN anywhere in the group takes the element-wise path
+// (torch.argmax treats NaN as the maximum; the sum becomes NaN either way).
+__device__ __forceinline__ void stat_add8(RowStat& a, const float (&x)[8], int j0, int stride) {
+  const float g = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += x[i];                       // NaN (or inf - inf) anywhere -> NaN
+  if (!(t == t) || g == -INFINITY || g == INFINITY) {          // rare: NaN, infinities
+#pragma unroll
+    for (int i = 0; i < 8; ++i) stat_add(a, x[i], j0 + (i >> 1) * stride + (i & 1));
+    return;
+  }
+  if (g > a.m) {
+    a.s *= __expf(a.m - g);                                    // exp(-inf) = 0 on the first group
+    a.m = g;
+  }
+  float e = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) e += __expf(x[i] - a.m);
+  a.s += e;
+  if (g > a.bv) {                                              // strictly greater: earlier columns keep ties
+    a.bv = g;
+#pragma unroll
+    for (int i = 7; i >= 0; --i)
+      if (x[i] == g) a.bi = j0 + (i >> 1) * stride + (i & 1);  // descending: the first column attaining g wins
+  }
+}
+
+// `VEC2`: V is even, so every row starts 8-byte aligned and is read as float2 (x[2q], x[2q+1] = columns j0 + q * stride
+// + {0, 1} with stride = 2 * RECON_THREADS); otherwise the scalar loop.
+template <bool VEC2>
 __global__ void __launch_bounds__(RECON_THREADS) recon_forward_kernel(const float* __restrict__ logits,
                                                                       const int64_t* __restrict__ ids, int64_t R, int V,
                                                                       int S, float* __restrict__ row_lse,
@@ -59,14 +93,31 @@ __global__ void __launch_bounds__(RECON_THREADS) recon_forward_kernel(const floa
   const float* x = logits + r * (int64_t)V;
   RowStat st;
   st.m = -INFINITY; st.s = 0.f; st.bv = -INFINITY; st.bi = 0;
-  int j = threadIdx.x;
-  for (; j + 3 * RECON_THREADS < V; j += 4 * RECON_THREADS) {
-    const float a = __ldg(x + j), b = __ldg(x + j + RECON_THREADS), c = __ldg(x + j + 2 * RECON_THREADS),
-                d = __ldg(x + j + 3 * RECON_THREADS);
-    stat_add(st, a, j); stat_add(st, b, j + RECON_THREADS);
-    stat_add(st, c, j + 2 * RECON_THREADS); stat_add(st, d, j + 3 * RECON_THREADS);
+  int j;
+  if constexpr (VEC2) {
+    constexpr int STRIDE = 2 * RECON_THREADS;                  // columns between a thread's consecutive float2 loads
+    const float2* x2 = reinterpret_cast<const float2*>(x);
+    j = 2 * threadIdx.x;
+    for (; j + 3 * STRIDE + 1 < V; j += 4 * STRIDE) {
+      const float2 a = __ldg(x2 + (j >> 1)), b = __ldg(x2 + ((j + STRIDE) >> 1)), c = __ldg(x2 + ((j + 2 * STRIDE) >> 1)),
+                   d = __ldg(x2 + ((j + 3 * STRIDE) >> 1));
+      const float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+      stat_add8(st, v, j, STRIDE);
+    }
+    for (; j + 1 < V; j += STRIDE) {
+      const float2 a = __ldg(x2 + (j >> 1));
+      stat_add(st, a.x, j); stat_add(st, a.y, j + 1);
+    }
+  } else {
+    j = threadIdx.x;
+    for (; j + 3 * RECON_THREADS < V; j += 4 * RECON_THREADS) {
+      const float a = __ldg(x + j), b = __ldg(x + j + RECON_THREADS), c = __ldg(x + j + 2 * RECON_THREADS),
+                  d = __ldg(x + j + 3 * RECON_THREADS);
+      stat_add(st, a, j); stat_add(st, b, j + RECON_THREADS);
+      stat_add(st, c, j + 2 * RECON_THREADS); stat_add(st, d, j + 3 * RECON_THREADS);
+    }
+    for (; j < V; j += RECON_THREADS) stat_add(st, __ldg(x + j), j);
   }
-  for (; j < V; j += RECON_THREADS) stat_add(st, __ldg(x + j), j);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     RowStat other;
@@ -166,7 +217,10 @@ int kvq_recon_loss_forward(const float* logits, const int64_t* ids, int64_t B, i
   KVQ_CUDA(cudaMemsetAsync(p, 0, 16, st));
   KVQ_CUDA(cudaMemsetAsync(per, 0, (size_t)B * 4, st));
   const int64_t R = B * S;
-  recon_forward_kernel<<<(unsigned)R, RECON_THREADS, 0, st>>>(logits, ids, R, (int)V, (int)S, row_lse, recon_ids, row_nll, total, per);
+  if (V % 2 == 0 && ((uintptr_t)logits & 7) == 0)
+    recon_forward_kernel<true><<<(unsigned)R, RECON_THREADS, 0, st>>>(logits, ids, R, (int)V, (int)S, row_lse, recon_ids, row_nll, total, per);
+  else
+    recon_forward_kernel<false><<<(unsigned)R, RECON_THREADS, 0, st>>>(logits, ids, R, (int)V, (int)S, row_lse, recon_ids, row_nll, total, per);
   KVQ_LAUNCH_CHECK();
   recon_finalize_kernel<<<1, 1024, 0, st>>>(row_nll, total, per, R, (int)S, B, loss, acc);
   KVQ_LAUNCH_CHECK();

@@ -97,6 +97,32 @@ def test_fused_recon_loss_matches_the_reference_expressions(B, S, V, scale):
     assert float(loss2) == float(loss)
 
 
+@pytest.mark.parametrize("V", [4098, 30522, 1001])
+def test_recon_argmax_ties_nan_and_infinities(V):
+    """arg-max semantics of torch.argmax on the grouped / vectorised path: first column on ties, the first NaN wins
+    outright, -inf logits contribute nothing, +inf is the maximum."""
+    k = _kvq()
+    g = torch.Generator(device=DEV).manual_seed(V)
+    logits = torch.randn(6, 2, V, device=DEV, generator=g)
+    x = logits.view(-1, V)
+    x[0, 700] = 50.0; x[0, 3000 % V] = 50.0; x[0, 5] = 50.0            # three equal maxima: column 5
+    x[1, 900] = float("nan"); x[1, 17] = float("nan")                   # NaN is the maximum, first one: column 17
+    x[2, :] = float("-inf"); x[2, 123] = 1.5                            # one finite logit
+    x[3, 600:700] = float("-inf")                                       # a stretch of -inf inside a normal row
+    x[4, 42] = float("inf")                                             # +inf
+    x[5, V - 1] = 60.0                                                  # maximum in the very last column (tail loop)
+    ids = torch.randint(0, V, (6, 2), device=DEV, generator=g)
+    loss, recon, acc, per = k.recon_loss(logits, ids)
+    want = torch.argmax(logits, dim=-1)
+    assert torch.equal(recon, want), (recon.flatten().tolist(), want.flatten().tolist())
+    rows = [0, 2, 3, 5] + list(range(6, 12))                            # rows whose log-softmax is finite
+    ref = -torch.log_softmax(x[rows].double(), dim=-1).gather(1, ids.view(-1, 1)[rows]).squeeze(1)
+    _, _, _, _, lse = torch.ops.kvq.recon_loss_forward(logits, ids)
+    got = lse[rows].double() - x[rows].double().gather(1, ids.view(-1, 1)[rows]).squeeze(1)
+    fin = torch.isfinite(ref)
+    assert torch.allclose(got[fin], ref[fin], rtol=1e-5, atol=1e-5)
+
+
 def test_recon_loss_inplace_scaling_and_compile():
     k = _kvq()
     V = 1000
