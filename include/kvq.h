@@ -233,10 +233,14 @@ int kvq_recon_loss_backward(const float* logits, const int64_t* ids, const float
  *
  * kvq_gemm_nt: C (M x ldc) = alpha * A (M x Kc) B^T (n x Kc) + bias[n] on the tcgen05 tf32 path (fp32 accumulate, TMA-fed,
  * the search kernel with a store epilogue).  A and B are dense row-major with leading dimension Kc; Kc % 32 == 0,
- * ldc % 4 == 0, columns [n, ldc) of C are written as zeros.  bias may be NULL.
+ * ldc % 4 == 0, columns [n, ldc) of C are written as zeros.  bias may be NULL.  A product with few output tiles and a
+ * long contraction (weight gradients) is cut into contraction ranges that run as separate work items, their partial
+ * products added in a fixed order from `workspace` (kvq_gemm_nt_workspace_bytes; 0 = never split for this shape;
+ * workspace NULL or too small = run unsplit).
  * kvq_transpose_pad: dst (C x ldd) = src^T for src (R x C, leading dimension lds); columns [R, ldd) are zero-filled. */
+size_t kvq_gemm_nt_workspace_bytes(int64_t M, int64_t n, int64_t Kc, int64_t ldc);
 int kvq_gemm_nt(const float* A, const float* B, int64_t M, int64_t n, int64_t Kc, float* C, int64_t ldc, const float* bias,
-                float alpha, kvq_stream_t stream);
+                float alpha, void* workspace, size_t workspace_bytes, kvq_stream_t stream);
 int kvq_transpose_pad(const float* src, int64_t R, int64_t C, int64_t lds, float* dst, int64_t ldd, kvq_stream_t stream);
 /* Per-row part of GumbelQuantizer.forward (:57-74) on logits (N x ldk, K valid columns):
  *   y_soft = softmax((logits + g) / tau); y = one_hot(argmax) - y_soft + y_soft (hard) or y_soft; ind = argmax;
@@ -253,8 +257,11 @@ int kvq_gumbel_hard_gather(const float* y, const int64_t* ind, const float* E, i
  * (may be NULL): softmax backward of both softmaxes, straight-through for the hard one-hot. */
 int kvq_gumbel_rows_backward(const float* logits, const float* noise, uint64_t seed, const float* dy, const float* g_diff,
                              int64_t N, int64_t K, int64_t ldk, float tau, float kld_scale, float* dL, kvq_stream_t stream);
-/* out[k] = sum_n a[n, k] for the first K columns of an (N x ld) matrix (the bias gradient), fixed summation order. */
-int kvq_colsum(const float* a, int64_t N, int64_t K, int64_t ld, float* out, kvq_stream_t stream);
+/* out[k] = sum_n a[n, k] for the first K columns of an (N x ld) matrix (the bias gradient), fixed summation order
+ * (two stages; the workspace holds the per-row-block partial sums). */
+size_t kvq_colsum_workspace_bytes(int64_t N, int64_t K);
+int kvq_colsum(const float* a, int64_t N, int64_t K, int64_t ld, float* out, void* workspace, size_t workspace_bytes,
+               kvq_stream_t stream);
 
 /* Token-id corruption helpers.  common/tensor_utils.py:13-49 and :52-87, with a counter-based device RNG
  * (seeded; the reference uses the host RNG, so parity is distributional: exact counts, value ranges).

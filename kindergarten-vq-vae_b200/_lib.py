@@ -53,13 +53,15 @@ SIGNATURES = {
     "kvq_recon_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "kvq_recon_loss_forward": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "kvq_recon_loss_backward": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P]),
-    "kvq_gemm_nt": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_float, _P]),
+    "kvq_gemm_nt_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
+    "kvq_gemm_nt": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_float, _P, c_size_t, _P]),
     "kvq_transpose_pad": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, _P]),
     "kvq_gumbel_rows_forward": (c_int, [_P, _P, c_uint64, c_int64, c_int64, c_int64, c_float, c_float, c_int, _P, _P, _P, _P,
                                         _P]),
     "kvq_gumbel_hard_gather": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, _P, _P]),
     "kvq_gumbel_rows_backward": (c_int, [_P, _P, c_uint64, _P, _P, c_int64, c_int64, c_int64, c_float, c_float, _P, _P]),
-    "kvq_colsum": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),
+    "kvq_colsum_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "kvq_colsum": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "kvq_replace_pct_rand_values": (c_int, [_P, c_int64, c_double, c_int64, c_int64, c_uint64, _P, _P]),
     "kvq_change_percentage_of_elements": (c_int, [_P, c_int64, c_int64, c_int, c_double, c_int64, c_int64, c_uint64,
                                                   _P, _P]),

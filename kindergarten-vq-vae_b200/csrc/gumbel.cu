@@ -220,22 +220,39 @@ __global__ void __launch_bounds__(256) gumbel_rows_backward_kernel(const float* 
   }
 }
 
-// column sums of an (N x ld) matrix, first K columns: out[k] = sum_n a[n,k].  Fixed summation order.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ a, int64_t N, int K, int64_t ld,
-                                                     float* __restrict__ out) {
+// column sums of an (N x ld) matrix, first K columns: out[k] = sum_n a[n,k], in two fixed-order stages (bitwise
+// reproducible): blocks of 32 columns x COLSUM_ROWS rows leave partial sums, one more kernel adds the row blocks in order.
+constexpr int COLSUM_ROWS = 512;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ a, int64_t N, int K, int64_t ld,
+                                                             float* __restrict__ partial) {
   __shared__ float part[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
-  float s = 0.f;
-  if (k < K)
-    for (int64_t n = w; n < N; n += 8) s += a[n * ld + k];
-  part[w][lane] = s;
+  const int64_t n0 = (int64_t)blockIdx.y * COLSUM_ROWS;
+  const int64_t n1 = n0 + COLSUM_ROWS < N ? n0 + COLSUM_ROWS : N;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // four loads in flight per thread
+  if (k < K) {
+    int64_t n = n0 + w;
+    for (; n + 24 < n1; n += 32) {
+      s0 += a[n * ld + k]; s1 += a[(n + 8) * ld + k]; s2 += a[(n + 16) * ld + k]; s3 += a[(n + 24) * ld + k];
+    }
+    for (; n < n1; n += 8) s0 += a[n * ld + k];
+  }
+  part[w][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (w == 0 && k < K) {
     float t = part[0][lane];
     for (int i = 1; i < 8; ++i) t += part[i][lane];
-    out[k] = t;
+    partial[(int64_t)blockIdx.y * K + k] = t;
   }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int row_blocks, int K,
+                                                           float* __restrict__ out) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= K) return;
+  float t = 0.f;
+  for (int b = 0; b < row_blocks; ++b) t += partial[(int64_t)b * K + k];
+  out[k] = t;
 }
 
 }  // namespace kvq
@@ -244,11 +261,17 @@ using namespace kvq;
 
 extern "C" {
 
+size_t kvq_gemm_nt_workspace_bytes(int64_t M, int64_t n, int64_t Kc, int64_t ldc) {
+  if (M < 0 || n < 0 || Kc < 1 || Kc > 0x7fffffffll || ldc < n) return 0;
+  return gemm_nt_tf32_workspace_bytes(M, n, (int)Kc, ldc);
+}
+
 int kvq_gemm_nt(const float* A, const float* B, int64_t M, int64_t n, int64_t Kc, float* C, int64_t ldc, const float* bias,
-                float alpha, kvq_stream_t stream) {
+                float alpha, void* workspace, size_t workspace_bytes, kvq_stream_t stream) {
   int rc = check_device(); if (rc) return rc;
   KVQ_REQUIRE(A && B && C && M >= 0 && n >= 0 && Kc >= 1 && Kc <= 0x7fffffffll, KVQ_ERR_ARG, "kvq_gemm_nt: bad arguments");
-  return launch_gemm_nt_tf32(A, B, M, n, (int)Kc, C, ldc, bias, alpha, (cudaStream_t)stream);
+  KVQ_REQUIRE(!workspace || ((uintptr_t)workspace & 15) == 0, KVQ_ERR_WORKSPACE, "kvq_gemm_nt: workspace must be 16-byte aligned");
+  return launch_gemm_nt_tf32(A, B, M, n, (int)Kc, C, ldc, bias, alpha, (cudaStream_t)stream, workspace, workspace_bytes);
 }
 
 int kvq_transpose_pad(const float* src, int64_t R, int64_t C, int64_t lds, float* dst, int64_t ldd, kvq_stream_t stream) {
@@ -298,10 +321,26 @@ int kvq_gumbel_rows_backward(const float* logits, const float* noise, uint64_t s
   return KVQ_OK;
 }
 
-int kvq_colsum(const float* a, int64_t N, int64_t K, int64_t ld, float* out, kvq_stream_t stream) {
+size_t kvq_colsum_workspace_bytes(int64_t N, int64_t K) {
+  if (N < 0 || K < 1) return 0;
+  const int64_t row_blocks = (N + COLSUM_ROWS - 1) / COLSUM_ROWS;
+  return align_up((size_t)(row_blocks > 0 ? row_blocks : 1) * (size_t)K * 4, 256);
+}
+
+int kvq_colsum(const float* a, int64_t N, int64_t K, int64_t ld, float* out, void* workspace, size_t workspace_bytes,
+               kvq_stream_t stream) {
   int rc = check_device(); if (rc) return rc;
-  KVQ_REQUIRE(a && out && N >= 0 && K >= 1 && ld >= K, KVQ_ERR_ARG, "kvq_colsum: bad arguments");
-  colsum_kernel<<<(unsigned)((K + 31) / 32), 256, 0, (cudaStream_t)stream>>>(a, N, (int)K, ld, out);
+  KVQ_REQUIRE(a && out && workspace && N >= 0 && K >= 1 && ld >= K && K <= 0x7fffffffll, KVQ_ERR_ARG, "kvq_colsum: bad arguments");
+  KVQ_REQUIRE(workspace_bytes >= kvq_colsum_workspace_bytes(N, K), KVQ_ERR_WORKSPACE, "kvq_colsum: workspace too small");
+  const int64_t row_blocks = (N + COLSUM_ROWS - 1) / COLSUM_ROWS;
+  KVQ_REQUIRE(row_blocks <= 65535, KVQ_ERR_SHAPE, "kvq_colsum: N=%lld too large", (long long)N);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = static_cast<float*>(workspace);
+  if (row_blocks > 0) {
+    colsum_partial_kernel<<<dim3((unsigned)((K + 31) / 32), (unsigned)row_blocks), 256, 0, st>>>(a, N, (int)K, ld, partial);
+    KVQ_LAUNCH_CHECK();
+  }
+  colsum_final_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(partial, (int)row_blocks, (int)K, out);
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }

@@ -207,7 +207,8 @@ int run_search(int mode, const float* z, const float* E, const float* e2, const 
                int64_t* idx, long long* scratch, cudaStream_t st, int* deferred = nullptr, void* tail_rec = nullptr);
 // C (M x ldc) = alpha * A (M x Kc) B^T (n x Kc) + bias on the tcgen05 tf32 path; Kc % 32 == 0, ldc % 4 == 0
 int launch_gemm_nt_tf32(const float* A, const float* B, int64_t M, int64_t n, int Kc, float* C, int64_t ldc,
-                        const float* bias, float alpha, cudaStream_t st);
+                        const float* bias, float alpha, cudaStream_t st, void* ws = nullptr, size_t ws_bytes = 0);
+size_t gemm_nt_tf32_workspace_bytes(int64_t M, int64_t n, int Kc, int64_t ldc);
 int launch_fill_keys(long long* keys, int64_t N, cudaStream_t st);
 int launch_keys_to_idx(const long long* keys, int64_t N, int64_t* idx, cudaStream_t st);
 // idx2 / e2max given: fused exact re-evaluation of the tf32 top-2 pair (idx is then rewritten where the runner-up wins)

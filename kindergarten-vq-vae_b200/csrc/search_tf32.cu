@@ -91,6 +91,11 @@ struct Params {
   float tau_c;          //   lie within tau_i = tau_c |z_i| max|E| + 2^-15 max|E|^2 of the row's running best
   long long* keys;
   PeerKeys peers;       // n > 0: MIN-combine the packed keys straight into every rank's buffer over NVLink
+  // Contraction split (EPI_STORE with a long contraction and few output tiles): every item is cut into csplit ranges of
+  // kb_per_split 32-element blocks of the contraction; range c writes its partial product at out + c * split_stride
+  // and gemm_split_reduce_kernel adds the ranges in order.  csplit = 1 elsewhere.
+  int csplit, kb_per_split;
+  int64_t split_stride;
   // EPI_STORE only: out (N x ldc) receives alpha * (z E^T) + bias for columns < K, zeros for columns in [K, ldc)
   float* out;
   int64_t ldc;
@@ -102,11 +107,20 @@ struct Item {
   int64_t m_group;
   int t_begin, t_end;
   int tail_ks;          // >= 0: tail item, its code-range number
+  int kb_begin, kb_end; // blocks of the contraction this item multiplies (all of them unless csplit > 1)
+  int cs;               // contraction range number
 };
 __device__ __forceinline__ Item decode_item(const Params& p, int64_t item) {
   Item it;
   int tiles;
   int ks;
+  it.cs = 0;
+  if (p.csplit > 1) {
+    it.cs = (int)(item % p.csplit);
+    item /= p.csplit;
+  }
+  it.kb_begin = it.cs * p.kb_per_split;
+  it.kb_end = min(p.num_kblocks, it.kb_begin + p.kb_per_split);
   if (item < p.main_items) {
     it.m_group = item / p.ksplit;
     ks = (int)(item % p.ksplit);
@@ -519,7 +533,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
           }
           __syncwarp();
         }
-        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
           if (p.resident && t == t_begin) {
             // Resident latent tile, replaced block by block: block kb of the previous item is free as soon as the MMAs
             // of that item's last code tile have read it, so the reload overlaps the rest of that tile instead of
@@ -568,7 +582,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
           mbar_wait(bar_tm_empty + 8 * acc, acc_phase ^ 1);   // every epilogue warp has drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-          for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
             if (p.resident && t == t_begin) mbar_wait(bar_a_full + 8 * kb, a_phase);   // block kb of this item's latents
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
@@ -581,7 +595,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                 // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                tc_mma_tf32<CG>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+                tc_mma_tf32<CG>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), ((kb - it.kb_begin) | k) != 0 ? 1u : 0u);
               }
               tc_commit<CG>(bar_empty + 8 * stage);           // stage reusable once these MMAs retire
               // last code tile of the item: latent block kb may be overwritten with the next item's
@@ -610,7 +624,7 @@ search_tf32_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_cons
       const int64_t m_group = it.m_group;
       const int t_begin = it.t_begin, t_end = it.t_end;
       const int64_t row = (m_group * CG + cta_rank) * BLOCK_M + row_in_tile;
-      float* orow = p.out + row * p.ldc;
+      float* orow = p.out + (int64_t)it.cs * p.split_stride + row * p.ldc;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(bar_tm_full + 8 * acc, acc_phase);
         tc_fence_after();
@@ -979,6 +993,7 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   p.tau_c = 1.25f * 0.00390625f * (tf32_operands_rounded() ? 1.f : 2.f);   // refine_bound_c2() uses 1.125: strictly wider
   if (peers) p.peers = *peers; else p.peers.n = 0;
   p.out = nullptr; p.ldc = 0; p.bias = nullptr; p.alpha = 1.f;
+  p.csplit = 1; p.kb_per_split = p.num_kblocks; p.split_stride = 0;
   constexpr bool TOP2 = (EPI == EPI_TOP2);
   if (TOP2) KVQ_REQUIRE(p.ksplit == 1 && !p.use_atomic && p.peers.n == 0 && idx && idx2, KVQ_ERR_UNSUPPORTED,
                         "tf32 top-2 search needs an unsplit, unsharded search");
@@ -1027,9 +1042,46 @@ static int launch_cg(const float* z, const float* E, const float* e2, int64_t N,
   return KVQ_OK;
 }
 
+// Contraction split of the plain GEMM: a product with few output tiles and a long contraction (the weight gradients
+// dW = dL^T z and dE = y^T g_zq of the Gumbel quantiser: 512 x 768 outputs over 24576 rows = 6 items of 768 blocks)
+// leaves most of the GPU idle, so the contraction is cut into ranges that run as separate items.
+static int store_csplit(int64_t M, int64_t Ncols, int Kc, int groups) {
+  if (Kc <= RESIDENT_MAX_D) return 1;                      // resident-tile mode multiplies the whole (short) contraction
+  const int n_tiles = (int)((Ncols + BLOCK_N - 1) / BLOCK_N);
+  const int64_t m_groups = ((M + BLOCK_M - 1) / BLOCK_M + 1) / 2;
+  int64_t items = m_groups;
+  if (m_groups < groups) items = m_groups * min_i64(n_tiles, (groups + m_groups - 1) / m_groups);
+  const int kblocks = Kc / BLOCK_K;
+  if (items * 2 > groups || kblocks < 32) return 1;
+  int cs = (int)min_i64(groups / items, kblocks / 16);     // at least 16 blocks (512 elements) per range
+  if (cs < 2) return 1;
+  const int per = (kblocks + cs - 1) / cs;
+  return (kblocks + per - 1) / per;
+}
+// C = alpha * (sum of the partial products, in order) + bias; columns [Ncols, ldc) = 0.  ldc % 4 == 0.
+__global__ void gemm_split_reduce_kernel(const float* __restrict__ part, int csplit, int64_t M, int64_t Ncols, int64_t ldc,
+                                         const float* __restrict__ bias, float alpha, float* __restrict__ C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index
+  const int64_t total = M * ldc / 4;
+  if (i >= total) return;
+  const int64_t c = (i * 4) % ldc;
+  float4 acc = reinterpret_cast<const float4*>(part)[i];
+  for (int s = 1; s < csplit; ++s) {
+    const float4 v = reinterpret_cast<const float4*>(part + (int64_t)s * M * ldc)[i];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float b = (bias && c + e < Ncols) ? __ldg(bias + c + e) : 0.f;
+    o[e] = (c + e < Ncols) ? fmaf(alpha, o[e], b) : 0.f;
+  }
+  reinterpret_cast<float4*>(C)[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 // C (M x ldc) = alpha * A (M x Kc) B^T (Ncols x Kc) + bias, tf32 products / fp32 accumulate; columns [Ncols, ldc) = 0.
 static int launch_store(const float* A, const float* B, int64_t M, int64_t Ncols, int Kc, float* C, int64_t ldc,
-                        const float* bias, float alpha, cudaStream_t st) {
+                        const float* bias, float alpha, cudaStream_t st, void* ws, size_t ws_bytes) {
   constexpr int CG = 2;
   constexpr int B_STAGE_BYTES = (BLOCK_N / CG) * BLOCK_K * 4;
   Params p;
@@ -1045,6 +1097,11 @@ static int launch_store(const float* A, const float* B, int64_t M, int64_t Ncols
   p.ksplit = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.n_items = m_groups * p.ksplit;
   p.main_items = p.n_items; p.tail_group0 = m_groups; p.tail_split = 1; p.tail_tiles = p.n_tiles; p.tail_rec = nullptr; p.tail_rows = 0;
+  p.csplit = store_csplit(M, Ncols, Kc, groups);
+  if (p.csplit > 1 && (!ws || ws_bytes < (size_t)p.csplit * (size_t)M * (size_t)ldc * 4)) p.csplit = 1;   // no room: unsplit
+  p.kb_per_split = (p.num_kblocks + p.csplit - 1) / p.csplit;
+  p.split_stride = M * ldc;
+  p.n_items *= p.csplit;
   p.resident = (Kc <= RESIDENT_MAX_D) ? 1 : 0;
   const int a_bytes = p.resident ? p.num_kblocks * A_KBLOCK_BYTES : 0;
   const int stage_bytes = p.resident ? B_STAGE_BYTES : (A_KBLOCK_BYTES + B_STAGE_BYTES);
@@ -1052,9 +1109,13 @@ static int launch_store(const float* A, const float* B, int64_t M, int64_t Ncols
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.stages = stages;
   p.use_atomic = 0;
-  p.e2 = nullptr; p.idx = nullptr; p.keys = nullptr; p.idx2 = nullptr;
+  p.e2 = nullptr; p.idx = nullptr; p.keys = nullptr; p.idx2 = nullptr; p.e2max = nullptr; p.tau_c = 0.f;
   p.peers.n = 0;
-  p.out = C; p.ldc = ldc; p.bias = bias; p.alpha = alpha;
+  const bool split = p.csplit > 1;
+  p.out = split ? static_cast<float*>(ws) : C;
+  p.ldc = ldc;
+  p.bias = split ? nullptr : bias;                          // applied by the reduction when the contraction is split
+  p.alpha = split ? 1.f : alpha;
   const size_t smem = 1024 + SMEM_CTRL_BYTES + (size_t)a_bytes + (size_t)stages * stage_bytes;
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, Kc, BLOCK_M, true);
@@ -1076,13 +1137,26 @@ static int launch_store(const float* A, const float* B, int64_t M, int64_t Ncols
   cfg.numAttrs = 1;
   count_launch();
   KVQ_CUDA(cudaLaunchKernelEx(&cfg, search_tf32_kernel<CG, EPI_STORE>, ma, mb, p));
+  if (split) {
+    count_launch();
+    const int64_t total = M * ldc / 4;
+    gemm_split_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(static_cast<const float*>(ws), p.csplit, M,
+                                                                            Ncols, ldc, bias, alpha, C);
+    KVQ_LAUNCH_CHECK();
+  }
   return KVQ_OK;
 }
 
 }  // namespace t5
 
+size_t gemm_nt_tf32_workspace_bytes(int64_t M, int64_t Ncols, int Kc, int64_t ldc) {
+  if (M <= 0 || Ncols <= 0 || Kc < 32) return 0;
+  const int cs = t5::store_csplit(M, Ncols, Kc, sm_count() / 2);
+  return cs > 1 ? align_up((size_t)cs * (size_t)M * (size_t)ldc * 4, 256) : 0;
+}
+
 int launch_gemm_nt_tf32(const float* A, const float* B, int64_t M, int64_t Ncols, int Kc, float* C, int64_t ldc,
-                        const float* bias, float alpha, cudaStream_t st) {
+                        const float* bias, float alpha, cudaStream_t st, void* ws, size_t ws_bytes) {
   if (M <= 0 || Ncols <= 0) return KVQ_OK;
   KVQ_REQUIRE(Kc >= 32 && Kc % 32 == 0 && Kc <= 1 << 22, KVQ_ERR_SHAPE,
               "kvq_gemm_nt: the contraction length must be a multiple of 32 (got %d)", Kc);
@@ -1090,7 +1164,7 @@ int launch_gemm_nt_tf32(const float* A, const float* B, int64_t M, int64_t Ncols
               (long long)ldc, (long long)Ncols);
   KVQ_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0, KVQ_ERR_ARG, "kvq_gemm_nt: A, B, C must be 16-byte aligned");
   KVQ_REQUIRE(M < (1ll << 31) - 256 && Ncols < (1ll << 31) - 256, KVQ_ERR_SHAPE, "kvq_gemm_nt: matrix too large");
-  return t5::launch_store(A, B, M, Ncols, Kc, C, ldc, bias, alpha, st);
+  return t5::launch_store(A, B, M, Ncols, Kc, C, ldc, bias, alpha, st, ws, ws_bytes);
 }
 
 bool tf32_operands_rounded() {

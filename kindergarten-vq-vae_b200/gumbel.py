@@ -33,8 +33,12 @@ def _up32(n: int) -> int:
 def _gemm_nt(A: Tensor, B: Tensor, M: int, n: int, Kc: int, ldc: int, bias: Optional[Tensor] = None) -> Tensor:
     """C (M x ldc) = A (M x Kc) B^T (n x Kc) + bias on the tensor cores (tf32, fp32 accumulate)."""
     C = torch.empty(M, ldc, dtype=torch.float32, device=A.device)
-    check(_lib.load().kvq_gemm_nt(A.data_ptr(), B.data_ptr(), M, n, Kc, C.data_ptr(), ldc,
-                                  None if bias is None else bias.data_ptr(), 1.0, _stream()), "kvq_gemm_nt")
+    lib = _lib.load()
+    nbytes = lib.kvq_gemm_nt_workspace_bytes(M, n, Kc, ldc)       # > 0: few output tiles, long contraction -> split
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device) if nbytes else None
+    check(lib.kvq_gemm_nt(A.data_ptr(), B.data_ptr(), M, n, Kc, C.data_ptr(), ldc,
+                          None if bias is None else bias.data_ptr(), 1.0, None if ws is None else ws.data_ptr(), nbytes,
+                          _stream()), "kvq_gemm_nt")
     return C
 
 
@@ -105,7 +109,9 @@ class _GumbelFn(torch.autograd.Function):
                 dW = _gemm_nt(dLT, XT, K, C, Np, C).view(K, C, 1)                       # dL^T z
             if ctx.needs_input_grad[2]:
                 db = torch.empty(K, dtype=torch.float32, device=X.device)
-                check(lib.kvq_colsum(dL.data_ptr(), N, K, Kp, db.data_ptr(), _stream()), "kvq_colsum")
+                cws = torch.empty(lib.kvq_colsum_workspace_bytes(N, K), dtype=torch.uint8, device=X.device)
+                check(lib.kvq_colsum(dL.data_ptr(), N, K, Kp, db.data_ptr(), cws.data_ptr(), cws.numel(), _stream()),
+                      "kvq_colsum")
             if ctx.needs_input_grad[3]:
                 if g_zq is None:
                     dE = torch.zeros_like(E)

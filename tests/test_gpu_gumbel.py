@@ -110,3 +110,38 @@ def test_gumbel_device_sample_is_gumbel_and_repeatable():
     assert sorted(gq.state_dict().keys()) == ["embed.weight", "proj.bias", "proj.weight"]
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         k.GumbelQuantizer(C, K, D, 1.0, 5e-4, True).forward(torch.randn(2, 3, C), True)
+
+
+@pytest.mark.parametrize("M,n,Kc", [(512, 768, 24576), (300, 100, 4096), (512, 512, 1024), (24576, 512, 768)])
+def test_gemm_nt_with_and_without_the_contraction_split(M, n, Kc):
+    """kvq_gemm_nt on skinny outputs with a long contraction (the weight-gradient shapes): the contraction is cut into
+    ranges added in a fixed order.  Same result as the unsplit run up to fp32 summation order, both within the tf32 bound
+    of the fp64 product; bias and the zero padding of columns [n, ldc) survive the split; bitwise reproducible."""
+    from kindergarten_vq_vae_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(M + n)
+    A = torch.randn(M, Kc, device=DEV, generator=g)
+    B = torch.randn(n, Kc, device=DEV, generator=g)
+    bias = torch.randn(n, device=DEV, generator=g)
+    ldc = (n + 31) // 32 * 32
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(with_ws):
+        C = torch.full((M, ldc), 7.0, device=DEV)
+        nbytes = lib.kvq_gemm_nt_workspace_bytes(M, n, Kc, ldc) if with_ws else 0
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=DEV)
+        _lib.check(lib.kvq_gemm_nt(A.data_ptr(), B.data_ptr(), M, n, Kc, C.data_ptr(), ldc, bias.data_ptr(), 0.5,
+                                   ws.data_ptr() if nbytes else None, nbytes, stream), "kvq_gemm_nt")
+        return C, nbytes
+    C_split, nbytes = run(True)
+    C_split2, _ = run(True)
+    C_plain, _ = run(False)
+    torch.cuda.synchronize()
+    assert (nbytes > 0) == (M * n <= 512 * 768 and Kc >= 1024)          # the skinny shapes split, the tall one does not
+    assert torch.equal(C_split, C_split2)
+    ref = 0.5 * (A.double() @ B.double().t()) + bias.double()
+    bound = 2.0 ** -9 * 0.5 * A.norm(dim=1).double()[:, None] * B.norm(dim=1).double()[None, :] + 1e-3
+    for C in (C_split, C_plain):
+        assert bool(((C[:, :n].double() - ref).abs() <= bound).all())
+        assert bool((C[:, n:] == 0).all())
+    assert float((C_split - C_plain).abs().max()) <= 1e-4 * float(ref.abs().max())

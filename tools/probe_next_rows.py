@@ -79,8 +79,37 @@ def main():
     Nn = 2048 * 12
     flops_f = 2.0 * Nn * K * 768 * 2            # logits + mix
     flops_b = 2.0 * Nn * K * 768 * 5            # dy, dz, dW, dE (+ the transposes' traffic)
+    # the reference's own tensor expressions (GumbelQuantizer.py:43-83) with torch on the same GPU
+    import torch.nn.functional as Fn
+    proj, embed = gq.proj, gq.embed
+
+    def ref_forward():
+        zt = z.permute(0, 2, 1)
+        logits = proj(zt)
+        soft = Fn.gumbel_softmax(logits, tau=1.0, dim=1, hard=False)
+        z_q = torch.einsum("b n s, n d -> b d s", soft, embed.weight)
+        qy = Fn.softmax(logits, dim=1)
+        diff = 5e-4 * torch.sum(qy * torch.log(qy * K + 1e-10), dim=1).mean()
+        ind = soft.argmax(dim=1)
+        return z_q.permute(0, 2, 1), diff, ind
+
+    def ref_fb():
+        z.grad = None
+        gq.zero_grad(set_to_none=True)
+        z_q, diff, ind = ref_forward()
+        torch.autograd.backward([z_q, diff], [gz, one])
+    ref = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        with torch.no_grad():
+            f = timed(ref_forward)
+        ref["allow_tf32" if tf32 else "fp32"] = {"fwd_ms": f, "fwd_bwd_ms": timed(ref_fb)}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     print(json.dumps({"row": "(f)4 GumbelQuantizer soft", "N": Nn, "K": K, "fwd_ms": ms_gf, "fwd_tflops": flops_f / ms_gf / 1e9,
-                      "fwd_bwd_ms": ms_gfb, "fwd_bwd_tflops": (flops_f + flops_b) / ms_gfb / 1e9}), flush=True)
+                      "fwd_bwd_ms": ms_gfb, "fwd_bwd_tflops": (flops_f + flops_b) / ms_gfb / 1e9,
+                      "reference_torch_ops_same_gpu": ref}), flush=True)
 
 
 if __name__ == "__main__":
