@@ -12,8 +12,8 @@
 // tcgen05 tf32 kernel of search_tf32.cu with its store epilogue (kvq_gemm_nt: C = A B^T); operands that are not
 // contraction-major are transposed (and zero-padded to the 32-element contraction granule) by transpose_pad_kernel.
 // Everything that is per-row -- the two softmaxes over K, the Gumbel sample, the straight-through value, the KL term,
-// the arg-max, and the softmax backward -- lives in the two row kernels below: one warp per latent row, the row of
-// K logits is read once into registers (K <= 32 * GQ_MAX_PER_LANE) or streamed twice.
+// the arg-max, and the softmax backward -- lives in the row kernels below: one warp per latent row; the row of K logits
+// (and its Gumbel sample) is formed once and kept in registers when K <= 512, else recomputed pass by pass.
 //
 // Gumbel sample: g = -log(e), e = -log(u) ~ Exp(1), u uniform in (0,1] from a counter-based generator keyed by
 // (seed, row, code); the backward regenerates the same sample from the same seed.  Tests pass the sample explicitly
@@ -123,6 +123,81 @@ __global__ void __launch_bounds__(256) gumbel_rows_forward_kernel(const float* _
   }
 }
 
+// The same rows for K <= 32 * GQ_PER_LANE (the reference's codebooks: a few hundred codes): each lane keeps its 16 perturbed
+// and plain logits in registers, so the Gumbel sample (two 64-bit mixes, two logarithms) and the divisions by tau are
+// formed once per element instead of once per pass -- the streaming kernel above spent 4/5 of its instructions there.
+// Per-lane summation order is unchanged, so the results are bitwise those of the streaming kernel.
+constexpr int GQ_PER_LANE = 16;
+__global__ void __launch_bounds__(256) gumbel_rows_forward_cached_kernel(const float* __restrict__ logits,
+                                                                         const float* __restrict__ noise, uint64_t seed,
+                                                                         int64_t N, int K, int64_t ldk, float tau, int hard,
+                                                                         float* __restrict__ y, int64_t* __restrict__ ind,
+                                                                         float* __restrict__ kl_row) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float* lr = logits + row * ldk;
+  const float* nr = noise ? noise + row * (int64_t)K : nullptr;
+  float* yr = y + row * ldk;
+  float a[GQ_PER_LANE], l[GQ_PER_LANE];
+  float m1 = -INFINITY, m2 = -INFINITY;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int i = 0; i < GQ_PER_LANE; ++i) {
+    const int k = lane + 32 * i;
+    a[i] = -INFINITY; l[i] = -INFINITY;
+    if (k < K) {
+      l[i] = lr[k];
+      const float g = nr ? nr[k] : gumbel_sample(seed, row, k, K);
+      a[i] = (l[i] + g) / tau;                          // (logits + gumbels) / tau exactly as the reference forms it
+      if (a[i] > m1 || (a[i] == m1 && k < bi) || (a[i] != a[i] && m1 == m1)) { m1 = a[i]; bi = k; }
+      m2 = fmaxf(m2, l[i]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m1, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    const bool on = om != om, mn = m1 != m1;
+    const bool take = (on || mn) ? (on && (!mn || oi < bi)) : (om > m1 || (om == m1 && oi < bi));
+    if (take) { m1 = om; bi = oi; }
+  }
+  m2 = warp_max(m2);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < GQ_PER_LANE; ++i) {
+    if (lane + 32 * i < K) {
+      a[i] = expf(a[i] - m1);
+      l[i] = expf(l[i] - m2);
+      s1 += a[i];
+      s2 += l[i];
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  float kl = 0.f;
+  const float Kf = (float)K;
+#pragma unroll
+  for (int i = 0; i < GQ_PER_LANE; ++i) {
+    const int k = lane + 32 * i;
+    if (k < ldk) {
+      float out = 0.f;
+      if (k < K) {
+        const float ys = a[i] / s1;
+        const float q = l[i] / s2;
+        kl += q * logf(q * Kf + 1e-10f);
+        out = hard ? ((((k == bi) ? 1.0f : 0.0f) - ys) + ys) : ys;
+      }
+      yr[k] = out;
+    }
+  }
+  kl = warp_sum(kl);
+  if (lane == 0) {
+    ind[row] = (int64_t)bi;
+    kl_row[row] = kl;
+  }
+}
+
 // diff = kld_scale * mean_n kl_row[n], summed in a fixed order (bitwise reproducible)
 __global__ void __launch_bounds__(1024) gumbel_kl_finalize_kernel(const float* __restrict__ kl_row, int64_t N, float kld_scale,
                                                                   float* __restrict__ diff) {
@@ -220,6 +295,81 @@ __global__ void __launch_bounds__(256) gumbel_rows_backward_kernel(const float* 
   }
 }
 
+// backward rows with the row cached in registers (K <= 32 * GQ_PER_LANE), see gumbel_rows_forward_cached_kernel
+__global__ void __launch_bounds__(256) gumbel_rows_backward_cached_kernel(const float* __restrict__ logits,
+                                                                          const float* __restrict__ noise, uint64_t seed,
+                                                                          const float* __restrict__ dy,
+                                                                          const float* __restrict__ g_diff, int64_t N, int K,
+                                                                          int64_t ldk, float tau, float kld_scale,
+                                                                          float* __restrict__ dL) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float* lr = logits + row * ldk;
+  const float* nr = noise ? noise + row * (int64_t)K : nullptr;
+  const float* dr = dy ? dy + row * ldk : nullptr;
+  float* outr = dL + row * ldk;
+  const float Kf = (float)K;
+  float a[GQ_PER_LANE], l[GQ_PER_LANE];
+  float m1 = -INFINITY, m2 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < GQ_PER_LANE; ++i) {
+    const int k = lane + 32 * i;
+    a[i] = -INFINITY; l[i] = -INFINITY;
+    if (k < K) {
+      l[i] = lr[k];
+      const float g = nr ? nr[k] : gumbel_sample(seed, row, k, K);
+      a[i] = (l[i] + g) / tau;
+      m1 = fmaxf(m1, a[i]);
+      m2 = fmaxf(m2, l[i]);
+    }
+  }
+  m1 = warp_max(m1);
+  m2 = warp_max(m2);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < GQ_PER_LANE; ++i) {
+    if (lane + 32 * i < K) {
+      a[i] = expf(a[i] - m1);
+      l[i] = expf(l[i] - m2);
+      s1 += a[i];
+      s2 += l[i];
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  float dot = 0.f, qh = 0.f;
+#pragma unroll
+  for (int i = 0; i < GQ_PER_LANE; ++i) {
+    const int k = lane + 32 * i;
+    if (k < K) {
+      a[i] = a[i] / s1;                                 // y_soft
+      l[i] = l[i] / s2;                                 // q
+      const float qk = l[i] * Kf;
+      if (dr) dot = fmaf(dr[k], a[i], dot);
+      qh = fmaf(l[i], logf(qk + 1e-10f) + qk / (qk + 1e-10f), qh);
+    }
+  }
+  dot = warp_sum(dot);
+  qh = warp_sum(qh);
+  const float gk = (g_diff ? *g_diff : 0.f) * kld_scale / (float)N;
+#pragma unroll
+  for (int i = 0; i < GQ_PER_LANE; ++i) {
+    const int k = lane + 32 * i;
+    if (k < ldk) {
+      float out = 0.f;
+      if (k < K) {
+        const float q = l[i];
+        const float qk = q * Kf;
+        const float h = logf(qk + 1e-10f) + qk / (qk + 1e-10f);
+        out = gk * q * (h - qh);
+        if (dr) out = fmaf(a[i] / tau, dr[k] - dot, out);
+      }
+      outr[k] = out;
+    }
+  }
+}
+
 // column sums of an (N x ld) matrix, first K columns: out[k] = sum_n a[n,k], in two fixed-order stages (bitwise
 // reproducible): blocks of 32 columns x COLSUM_ROWS rows leave partial sums, one more kernel adds the row blocks in order.
 constexpr int COLSUM_ROWS = 512;
@@ -292,8 +442,12 @@ int kvq_gumbel_rows_forward(const float* logits, const float* noise, uint64_t se
   KVQ_REQUIRE(logits && y && ind && diff && kl_row && N >= 1 && K >= 1 && K <= 0x7fffffffll && ldk >= K && tau > 0.f,
               KVQ_ERR_ARG, "kvq_gumbel_rows_forward: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  gumbel_rows_forward_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(logits, noise, seed, N, (int)K, ldk, tau, hard, y,
-                                                                    ind, kl_row);
+  if (ldk <= 32 * GQ_PER_LANE)
+    gumbel_rows_forward_cached_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(logits, noise, seed, N, (int)K, ldk, tau, hard,
+                                                                             y, ind, kl_row);
+  else
+    gumbel_rows_forward_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(logits, noise, seed, N, (int)K, ldk, tau, hard, y,
+                                                                      ind, kl_row);
   KVQ_LAUNCH_CHECK();
   gumbel_kl_finalize_kernel<<<1, 1024, 0, st>>>(kl_row, N, kld_scale, diff);
   KVQ_LAUNCH_CHECK();
@@ -315,8 +469,12 @@ int kvq_gumbel_rows_backward(const float* logits, const float* noise, uint64_t s
   int rc = check_device(); if (rc) return rc;
   KVQ_REQUIRE(logits && dL && N >= 1 && K >= 1 && K <= 0x7fffffffll && ldk >= K && tau > 0.f, KVQ_ERR_ARG,
               "kvq_gumbel_rows_backward: bad arguments");
-  gumbel_rows_backward_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, noise, seed, dy, g_diff, N,
-                                                                                       (int)K, ldk, tau, kld_scale, dL);
+  if (ldk <= 32 * GQ_PER_LANE)
+    gumbel_rows_backward_cached_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        logits, noise, seed, dy, g_diff, N, (int)K, ldk, tau, kld_scale, dL);
+  else
+    gumbel_rows_backward_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, noise, seed, dy, g_diff, N,
+                                                                                         (int)K, ldk, tau, kld_scale, dL);
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }
