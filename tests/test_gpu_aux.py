@@ -156,6 +156,10 @@ def test_kmeans2_matches_scipy_given_the_same_initial_centroids():
     assert torch.equal(l.cpu(), torch.from_numpy(ref_l).long())
     assert torch.allclose(c.cpu(), torch.from_numpy(ref_c), rtol=1e-5, atol=1e-5)
     assert torch.equal(c[15].cpu(), init[15])                                # empty cluster keeps its position
+    # the tensor-core search with its exact float64 re-evaluation of the two best centroids assigns the same labels
+    ca, la = k.kmeans2(data.to(DEV), init.to(DEV), iter=10, minit="matrix", search="auto")
+    assert torch.equal(la.cpu(), torch.from_numpy(ref_l).long())
+    assert torch.allclose(ca.cpu(), torch.from_numpy(ref_c), rtol=1e-5, atol=1e-5)
     # minit='points': centroids are data points after 0 iterations, K distinct rows, reproducible per seed
     c0, _ = k.kmeans2(data.to(DEV), 9, iter=0, minit="points", seed=5)
     assert c0.shape == (9, 64) and all(bool((data == r).all(1).any()) for r in c0.cpu())

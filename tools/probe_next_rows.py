@@ -52,7 +52,7 @@ def main():
     # ---- (f)1 k-means codebook init, vq_codebook_init_weights.py:79-101: BERT latents of 8192 sentences x 12 tokens, K = 512
     N, D, K = 8192 * 12, 768, 512
     data = torch.randn(N, D, device=dev, generator=g)
-    for search in ("fp32", "tf32"):
+    for search in ("auto", "fp32", "tf32"):
         ms = timed(lambda: kvq.kmeans2(data, K, iter=10, seed=1, search=search), warm=1, iters=3)
         print(json.dumps({"row": "(f)1 kmeans2", "N": N, "D": D, "K": K, "iter": 10, "search": search, "ms": ms,
                           "ms_per_iteration": ms / 10, "hbm_floor_ms_per_iteration": 2 * 4.0 * N * D / HBM_GBS / 1e6}), flush=True)
