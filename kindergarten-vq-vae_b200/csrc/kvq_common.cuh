@@ -103,6 +103,10 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+__device__ __forceinline__ void st_stream2(float2* p, const float2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
 // ---- per-warp shared-memory row rings fed by cp.async.bulk (the HBM-bound kernels) -----------------------------
 // A lane-elected producer copies whole rows (global -> shared) with the bulk-copy engine, completion counted on an
 // mbarrier per stage; the warp consumes a stage once its barrier phase flips.  No registers are tied up by bytes in

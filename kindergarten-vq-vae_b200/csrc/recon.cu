@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(1024) recon_finalize_kernel(const float* __res
   }
 }
 
+template <bool VEC2>
 __global__ void __launch_bounds__(RECON_THREADS) recon_backward_kernel(const float* __restrict__ logits,
                                                                        const int64_t* __restrict__ ids,
                                                                        const float* __restrict__ row_lse,
@@ -181,10 +182,37 @@ __global__ void __launch_bounds__(RECON_THREADS) recon_backward_kernel(const flo
   const float g = (g_loss ? *g_loss : 1.f) / (float)R;
   const int64_t id = ids[r];
   const bool counted = id >= 0 && id < V;                      // rows with an invalid target contribute nothing
-  for (int j = threadIdx.x; j < V; j += RECON_THREADS) {
-    float p = counted ? __expf(__ldg(x + j) - lse) : 0.f;
-    if (j == id) p -= 1.f;
-    dx[j] = g * p;
+  if constexpr (VEC2) {                                        // V even: rows are 8-byte aligned, two logits per access
+    const float2* x2 = reinterpret_cast<const float2*>(x);
+    float2* d2 = reinterpret_cast<float2*>(dx);
+    const int half = V >> 1;
+    int j = threadIdx.x;
+    for (; j + 3 * RECON_THREADS < half; j += 4 * RECON_THREADS) {          // four loads in flight per thread
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(x2 + j + u * RECON_THREADS);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = 2 * (j + u * RECON_THREADS);
+        float p0 = counted ? __expf(v[u].x - lse) : 0.f, p1 = counted ? __expf(v[u].y - lse) : 0.f;
+        if (c == id) p0 -= 1.f;
+        if (c + 1 == id) p1 -= 1.f;
+        st_stream2(d2 + j + u * RECON_THREADS, make_float2(g * p0, g * p1));
+      }
+    }
+    for (; j < half; j += RECON_THREADS) {
+      const float2 v = __ldg(x2 + j);
+      float p0 = counted ? __expf(v.x - lse) : 0.f, p1 = counted ? __expf(v.y - lse) : 0.f;
+      if (2 * j == id) p0 -= 1.f;
+      if (2 * j + 1 == id) p1 -= 1.f;
+      st_stream2(d2 + j, make_float2(g * p0, g * p1));
+    }
+  } else {
+    for (int j = threadIdx.x; j < V; j += RECON_THREADS) {
+      float p = counted ? __expf(__ldg(x + j) - lse) : 0.f;
+      if (j == id) p -= 1.f;
+      dx[j] = g * p;
+    }
   }
 }
 
@@ -233,8 +261,12 @@ int kvq_recon_loss_backward(const float* logits, const int64_t* ids, const float
   KVQ_REQUIRE(logits && ids && row_lse && dlogits, KVQ_ERR_ARG, "kvq_recon_loss_backward: null pointer");
   KVQ_REQUIRE(B >= 1 && S >= 1 && V >= 1 && V <= 0x7fffffffll && B * S <= 0x7fffffffll, KVQ_ERR_SHAPE,
               "kvq_recon_loss_backward: bad shape");
-  recon_backward_kernel<<<(unsigned)(B * S), RECON_THREADS, 0, (cudaStream_t)stream>>>(logits, ids, row_lse, g_loss, B * S,
-                                                                                      (int)V, dlogits);
+  if (V % 2 == 0 && (((uintptr_t)logits | (uintptr_t)dlogits) & 7) == 0)
+    recon_backward_kernel<true><<<(unsigned)(B * S), RECON_THREADS, 0, (cudaStream_t)stream>>>(logits, ids, row_lse, g_loss,
+                                                                                              B * S, (int)V, dlogits);
+  else
+    recon_backward_kernel<false><<<(unsigned)(B * S), RECON_THREADS, 0, (cudaStream_t)stream>>>(logits, ids, row_lse, g_loss,
+                                                                                               B * S, (int)V, dlogits);
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }
