@@ -1,6 +1,8 @@
 // HBM-bound forward kernels of the VQ layer: code norms, gather + straight-through + loss + histogram,
 // finalisation (loss, perplexity), dense one-hot on request, packed-key utilities, token accuracy.
 // Reference lines replaced: models/shelgon3/VectorQuantizer.py:60, :67-72, :76-85; common/metrics.py:8-36.
+#include <cooperative_groups.h>
+
 #include "kvq_common.cuh"
 
 namespace kvq {
@@ -535,18 +537,44 @@ int launch_quantize(const float* z, const float* E, int64_t* idx, int64_t N, int
 // ------------------------------------------------------------------------------------------------
 // loss and perplexity from the two reductions (VectorQuantizer.py:76-77 value, :84-85).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ sq_sum,
-                                                        const int32_t* __restrict__ hist, int64_t n_global, int D,
-                                                        int64_t K, float beta, float* __restrict__ loss,
-                                                        float* __restrict__ perplexity) {
+// One thread-block cluster of FIN_CLUSTER blocks: each block reduces its share of the histogram, block 0 adds the block
+// sums in rank order through distributed shared memory -- parallel over 8 SMs, fixed order (bitwise reproducible), no
+// scratch buffer.  (One block took 43 us at K = 65536 and 0.5 ms at the sharded codebook's K = 2^20.)
+constexpr int FIN_CLUSTER = 8;
+__device__ __forceinline__ double cluster_ordered_sum(double block_sum, double* slot) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  if (threadIdx.x == 0) *slot = block_sum;
+  cluster.sync();
+  double t = 0.0;
+  if (cluster.block_rank() == 0 && threadIdx.x == 0)
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) t += *cluster.map_shared_rank(slot, r);
+  cluster.sync();                                     // nobody exits while its shared memory may still be read
+  return t;                                           // valid in thread 0 of block 0
+}
+__device__ __forceinline__ double block_ordered_sum(double s, double* part /* [32] */) {
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+  return t;                                           // valid in thread 0
+}
+
+__global__ void __cluster_dims__(FIN_CLUSTER, 1, 1) __launch_bounds__(1024)
+finalize_kernel(const double* __restrict__ sq_sum, const int32_t* __restrict__ hist, int64_t n_global, int D, int64_t K,
+                float beta, float* __restrict__ loss, float* __restrict__ perplexity) {
   __shared__ double part[32];
+  __shared__ double slot;
   const float n_f = (float)n_global;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
   double s = 0.0;
-  for (int64_t k0 = threadIdx.x; k0 < K; k0 += 8 * (int64_t)blockDim.x) {
+  for (int64_t k0 = tid; k0 < K; k0 += 8 * nthr) {
     int32_t c[8];                                    // eight independent loads in flight per thread
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int64_t k = k0 + u * (int64_t)blockDim.x;
+      const int64_t k = k0 + u * nthr;
       c[u] = k < K ? hist[k] : 0;
     }
 #pragma unroll
@@ -555,12 +583,8 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
       s += (double)(p * logf(p + 1e-10f));           // an empty (or out-of-range) slot contributes 0 * log(1e-10) = 0
     }
   }
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+  const double t = cluster_ordered_sum(block_ordered_sum(s, part), &slot);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     *perplexity = expf(-(float)t);
     const float m = (float)(*sq_sum / ((double)n_global * (double)D));
     *loss = m + beta * m;
@@ -575,24 +599,22 @@ __global__ void __launch_bounds__(256) pack_partials_kernel(const double* __rest
   if (i == 0) packed[0] = *sq_sum;
   if (i < K) packed[1 + i] = (double)hist[i];
 }
-__global__ void __launch_bounds__(1024) finalize_packed_kernel(const double* __restrict__ packed, int64_t n_global, int D,
-                                                               int64_t K, float beta, float* __restrict__ loss,
-                                                               float* __restrict__ perplexity, int32_t* __restrict__ hist_out) {
+__global__ void __cluster_dims__(FIN_CLUSTER, 1, 1) __launch_bounds__(1024)
+finalize_packed_kernel(const double* __restrict__ packed, int64_t n_global, int D, int64_t K, float beta,
+                       float* __restrict__ loss, float* __restrict__ perplexity, int32_t* __restrict__ hist_out) {
   __shared__ double part[32];
+  __shared__ double slot;
   const float n_f = (float)n_global;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
   double s = 0.0;
-  for (int64_t k = threadIdx.x; k < K; k += blockDim.x) {
+  for (int64_t k = tid; k < K; k += nthr) {
     const int32_t c = (int32_t)packed[1 + k];
     if (hist_out) hist_out[k] = c;
     const float p = (float)c / n_f;
     s += (double)(p * logf(p + 1e-10f));
   }
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+  const double t = cluster_ordered_sum(block_ordered_sum(s, part), &slot);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     *perplexity = expf(-(float)t);
     const float m = (float)(packed[0] / ((double)n_global * (double)D));
     *loss = m + beta * m;
@@ -605,14 +627,14 @@ int launch_pack_partials(const double* sq_sum, const int32_t* hist, int64_t K, d
 }
 int launch_finalize_packed(const double* packed, int64_t n_global, int D, int64_t K, float beta, float* loss,
                            float* perplexity, int32_t* hist_out, cudaStream_t st) {
-  finalize_packed_kernel<<<1, 1024, 0, st>>>(packed, n_global, D, K, beta, loss, perplexity, hist_out);
+  finalize_packed_kernel<<<FIN_CLUSTER, 1024, 0, st>>>(packed, n_global, D, K, beta, loss, perplexity, hist_out);
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }
 
 int launch_finalize(const double* sq_sum, const int32_t* hist, int64_t n_global, int D, int64_t K, float beta,
                     float* loss, float* perplexity, cudaStream_t st) {
-  finalize_kernel<<<1, 1024, 0, st>>>(sq_sum, hist, n_global, D, K, beta, loss, perplexity);
+  finalize_kernel<<<FIN_CLUSTER, 1024, 0, st>>>(sq_sum, hist, n_global, D, K, beta, loss, perplexity);
   KVQ_LAUNCH_CHECK();
   return KVQ_OK;
 }
